@@ -1,0 +1,35 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE (oracle). Builds the UNMODIFIED reference from /root/reference into oracle/_ref/.
+#   cpu : reference CPU path (-DHAS_NO_CUDA, the reference's own fallback; SURVEY.md §8c recipe)
+#   gen : the reference's FD example generator (example/tfqmrgpu_generate_FD_example.cxx)
+#   gpu : reference CUDA kernels compiled for sm_100 (same-box GPU baseline; optional)
+# Sources are compiled where they lie; nothing is copied. Outputs go to oracle/_ref/ only (git-ignored).
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="${TFQMR_REFERENCE:-/root/reference}"
+OUT="$HERE/_ref"
+[ -d "$REF/tfQMRgpu" ] || { echo "reference not present at $REF - nothing built"; exit 0; }
+mkdir -p "$OUT"
+INC="-I$REF/tfQMRgpu/include -I$REF/tfQMRgpu/source -I$REF/third_party/rapidxml-1.13"
+# plain -O1/-O2 miscompile the reference's out-of-bounds flattened indexing (UB); these flags agree with -O0
+SAFE="-O3 -fno-tree-dce -fno-aggressive-loop-optimizations -fno-strict-aliasing"
+what="${1:-all}"
+if [ "$what" = all ] || [ "$what" = cpu ]; then
+  g++ -std=c++14 $SAFE -fopenmp -fPIC -shared -DHAS_NO_CUDA -include "$HERE/ref_shim.h" $INC \
+      -x c++ "$REF/tfQMRgpu/source/tfqmrgpu.cu" -x none "$HERE/ref_harness.cpp" -DHARNESS_NO_CUDA \
+      -o "$OUT/libtfqmr_ref_cpu.so"
+  echo "built $OUT/libtfqmr_ref_cpu.so"
+fi
+if [ "$what" = all ] || [ "$what" = gen ]; then
+  g++ -std=c++14 $SAFE -D__MAIN__ -include cstdint -include cmath -include cstdlib $INC \
+      "$REF/example/tfqmrgpu_generate_FD_example.cxx" -o "$OUT/generate_FD_example"
+  echo "built $OUT/generate_FD_example"
+fi
+if [ "$what" = all ] || [ "$what" = gpu ]; then
+  if command -v nvcc >/dev/null; then
+    nvcc -std=c++14 -O2 -arch=sm_100 -Xcompiler=-fopenmp,-fPIC,-fno-tree-dce,-fno-aggressive-loop-optimizations \
+        -include cstdint $INC -shared "$REF/tfQMRgpu/source/tfqmrgpu.cu" "$HERE/ref_harness.cpp" \
+        -o "$OUT/libtfqmr_ref_gpu.so" -lcurand
+    echo "built $OUT/libtfqmr_ref_gpu.so"
+  fi
+fi
