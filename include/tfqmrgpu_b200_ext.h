@@ -1,0 +1,68 @@
+/*
+ * tfqmrgpu_b200_ext.h - non-breaking extensions of the tfqmrgpu C-ABI (prefix tfqmrgpux_).
+ *
+ * None of these symbols exist in the reference; callers that only use tfqmrgpu.h never see them.
+ * They expose what the parity tests, the multi-GPU (RHS block-column sharded) driver and the
+ * benchmark need:  the device-built plan lists (bit-exact comparison with the reference's
+ * createPlan, tfqmrgpu.cu:183-314), injection of the random shadow vector v3 (the reference draws
+ * it inside setBuffer, tfqmrgpu.cu:430-442), the bare block-sparse product Y = A*X (the
+ * `bench_tfqmrgpu multi` role, bench_tfqmrgpu.cu:289-440) and counters.
+ */
+#ifndef TFQMRGPU_B200_EXT_H
+#define TFQMRGPU_B200_EXT_H
+
+#include "tfqmrgpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* library version of this implementation (the reference ships SOVERSION 1, VERSION 0.0.1) */
+tfqmrgpuStatus_t tfqmrgpux_getVersion(int *major, int *minor, int *patch);
+
+/* chatter on stdout: 0 silent (default), 1 reference-like "# norms of B ..." lines, 2 debug.
+ * Also settable with the environment variable TFQMRGPU_VERBOSE. */
+tfqmrgpuStatus_t tfqmrgpux_setVerbosity(int level);
+
+/* Plan lists, copied to HOST memory.  kind: 0 starts u32[nnzbX+1], 1 pairs u32[2*nPairs],
+ * 2 subset u32[nnzbB], 3 colindx u16[nnzbX]  (the four lists of the reference plan,
+ * tfqmrgpu_plan.hxx:20-50), 4 perm u32[nnzbX] (X block index in caller order -> internal,
+ * column-sorted, storage index), 5 colstart u32[nCols+1].
+ * *count receives the number of elements; out may be NULL to query the count only. */
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getPlanArray(tfqmrgpuBsrsvPlan_t plan, int kind, void *out, size_t *count);
+
+/* info[0..15] = nnzbX, nnzbB, nnzbA, nCols, nPairs, LM, LN, precision char, number of vector tiles,
+ * number of SpMM units, SpMM columns per unit, SpMM entries, mb, 0, 0, 0 */
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getPlanInfo(tfqmrgpuBsrsvPlan_t plan, int64_t info[16]);
+
+/* Random shadow vector v3, float[nnzbX][2][LM][LN] in the caller's X block order (= the layout the
+ * reference's cuRAND stream fills).  set: after setBuffer; onDevice != 0 if v3 is a device pointer. */
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setV3(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, float const *v3, int onDevice);
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getV3(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, float *v3Host);
+
+/* Y := A*X on the plan's vectors (X = what setMatrix('X') uploaded or the last solution),
+ * repeated nrep times on the handle's stream; asynchronous.  Fetch with getVector('Y'). */
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_multiply(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, int nrep);
+
+/* like tfqmrgpu_bsrsv_getMatrix but for var 'X' or 'Y' (the product of tfqmrgpux_bsrsv_multiply /
+ * the residual vector of the last probe).  Blocking. */
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getVector(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, char var,
+    void *val, char precision, char trans, tfqmrgpuDataLayout_t layout);
+
+/* byte window of an operand inside the caller's workspace.  var 'X' (solution, internal column-sorted
+ * block order, real_t[nnzbX][2][LM][LN]), 'A', 'B', '3' (v3), 'Y'.  Lets a multi-GPU driver gather X
+ * slices device-to-device (NCCL) without a host round trip. */
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getWindow(tfqmrgpuBsrsvPlan_t plan, char var, size_t *offset, size_t *length);
+
+/* per right-hand-side status int8[nCols*LN] after a solve: 0 ok, -1/-2/-3 breakdown codes of
+ * linalg.hxx:57,123,209, +1 exact zero residual (core.hxx:282-285).  Blocking. */
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getRhsStatus(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, int8_t *statusHost);
+
+/* stats[0..7] of the last solve: probes executed, kernels launched, iteration bodies enqueued,
+ * host wall milliseconds inside solve, last max_bound^2, last target_bound^2, 0, 0 */
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getSolveStats(tfqmrgpuBsrsvPlan_t plan, double stats[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFQMRGPU_B200_EXT_H */

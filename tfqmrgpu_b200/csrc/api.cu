@@ -1,0 +1,493 @@
+// The C-ABI of libtfQMRgpu.so: the 21 entry points of tfqmrgpu.h plus the tfqmrgpux_ extensions.
+// Behavioural reference: tfQMRgpu/source/tfqmrgpu.cu (cited per function).
+#include "tfq_internal.hpp"
+#include <curand.h>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+namespace tfq {
+
+const int kAllowedBlockSizes[15][2] = { // allowed_block_sizes.h:4-18, same order
+    {4, 4}, {4, 5}, {4, 8}, {4, 32}, {8, 8}, {8, 9}, {8, 10}, {8, 32}, {8, 64},
+    {16, 16}, {16, 32}, {16, 64}, {32, 32}, {32, 64}, {64, 64}};
+
+bool block_size_allowed(int lm, int ln) {
+    for (auto const &bs : kAllowedBlockSizes) if (bs[0] == lm && bs[1] == ln) return true;
+    return false;
+}
+
+static int g_verbosity = -1;
+int verbosity() {
+    if (g_verbosity < 0) {
+        char const *e = std::getenv("TFQMRGPU_VERBOSE");
+        g_verbosity = e ? std::atoi(e) : 0;
+    }
+    return g_verbosity;
+}
+void set_verbosity(int level) { g_verbosity = level < 0 ? 0 : level; }
+
+static inline Plan* P(tfqmrgpuBsrsvPlan_t plan) { return reinterpret_cast<Plan*>(plan); }
+static inline char lower(char c) { return char(c | 32); } // the reference's "| IgnoreCase" (util.hxx:12)
+
+// random shadow vector: cuRAND XORWOW, seed 1234, generated in the caller's block order like the
+// reference (linalg.hxx:777-797), then moved into column-sorted storage order
+static tfqmrgpuStatus_t fill_v3(Plan &p, cudaStream_t stream) {
+    size_t const n = size_t(p.nnzbX)*2*p.LM*p.LN;
+    float *const scratch = ws<float>(p, p.off_v[9]);
+    curandGenerator_t gen;
+    if (CURAND_STATUS_SUCCESS != curandCreateGenerator(&gen, CURAND_RNG_PSEUDO_DEFAULT)) return TFQ_ERR(TFQMRGPU_STATUS_RANDOM_GEN_FAILED);
+    tfqmrgpuStatus_t st = TFQMRGPU_STATUS_SUCCESS;
+    if (CURAND_STATUS_SUCCESS != curandSetStream(gen, stream)) st = TFQ_ERR(TFQMRGPU_STATUS_RANDOM_GEN_FAILED);
+    else if (CURAND_STATUS_SUCCESS != curandSetPseudoRandomGeneratorSeed(gen, 1234ull)) st = TFQ_ERR(TFQMRGPU_STATUS_RANDOM_GEN_FAILED);
+    else if (CURAND_STATUS_SUCCESS != curandGenerateUniform(gen, scratch, n)) st = TFQ_ERR(TFQMRGPU_STATUS_RANDOM_GEN_FAILED);
+    if (TFQMRGPU_STATUS_SUCCESS == st) st = permute_v3(p, ws<float>(p, p.off_v[3]), scratch, true, stream);
+    cudaStreamSynchronize(stream); // the generator must outlive its asynchronous work
+    curandDestroyGenerator(gen);
+    return st;
+}
+
+// shared by setMatrix/getMatrix/getVector: parse layout and transposition (tfqmrgpu.cu:480-501)
+static tfqmrgpuStatus_t parse_layout_trans(tfqmrgpuDataLayout_t layout, char transposition, bool &trans, double &scal_imag) {
+    switch (layout) {
+        case TFQMRGPU_LAYOUT_RRRRIIII: case TFQMRGPU_LAYOUT_RIRIRIRI: case TFQMRGPU_LAYOUT_RRIIRRII: break;
+        default: return TFQMRGPU_DATALAYOUT_UNKNOWN + TFQMRGPU_CODE_LINE*layout;
+    }
+    scal_imag = 1;
+    switch (lower(transposition)) {
+        case 'h': case 'c': scal_imag = -1; trans = true; break;
+        case '*':           scal_imag = -1; trans = false; break;
+        case 't': trans = true; break;
+        case 'n': trans = false; break;
+        default: return TFQ_ERRC(TFQMRGPU_TANSPOSITION_UNKNOWN, lower(transposition));
+    }
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+static tfqmrgpuStatus_t download_vector(Handle *h, Plan &p, size_t off_vec, void *val, char precision, char transposition,
+                                        tfqmrgpuDataLayout_t layout) {
+    bool trans = false; double scal_imag = 1;
+    tfqmrgpuStatus_t st = parse_layout_trans(layout, transposition, trans, scal_imag);
+    if (st) return st;
+    if (p.nnzbX < 1) return TFQMRGPU_STATUS_SUCCESS;
+    if (nullptr == p.pBuffer || nullptr == val) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    bool const is_double = ('z' == p.precision);
+    if (('z' == lower(precision)) != is_double) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, precision);
+    // out of place through a scratch vector, so the device copy keeps its solver layout
+    // (the reference transposes X in place and leaves it in host layout, tfqmrgpu.cu:552-600)
+    size_t const off_scratch = (off_vec == p.off_v[9]) ? p.off_v[8] : p.off_v[9];
+    st = convert_permuted(p, p.pBuffer + off_scratch, p.pBuffer + off_vec, p.nnzbX, p.LM, p.LN, is_double, layout, trans, scal_imag, false, h->stream);
+    if (st) return st;
+    TFQ_CUDA(cudaMemcpyAsync(val, p.pBuffer + off_scratch, p.vecBytes, cudaMemcpyDeviceToHost, h->stream));
+    TFQ_CUDA(cudaStreamSynchronize(h->stream));
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+} // namespace tfq
+
+using namespace tfq;
+
+extern "C" {
+
+// ---- handle / stream: tfqmrgpu.cu:110-134 -----------------------------------------------------------
+tfqmrgpuStatus_t tfqmrgpuCreateHandle(tfqmrgpuHandle_t *handle) {
+    if (nullptr == handle) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+    if (nullptr != *handle) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+    Handle *h = new (std::nothrow) Handle();
+    if (nullptr == h) return TFQ_ERR(TFQMRGPU_STATUS_ALLOCATION_FAILED);
+    *handle = h;
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+tfqmrgpuStatus_t tfqmrgpuDestroyHandle(tfqmrgpuHandle_t handle) {
+    if (nullptr == handle) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+    delete static_cast<Handle*>(handle);
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+tfqmrgpuStatus_t tfqmrgpuSetStream(tfqmrgpuHandle_t handle, cudaStream_t const streamId) {
+    if (nullptr == handle) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    static_cast<Handle*>(handle)->stream = streamId;
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+tfqmrgpuStatus_t tfqmrgpuGetStream(tfqmrgpuHandle_t handle, cudaStream_t *streamId) {
+    if (nullptr == handle || nullptr == streamId) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    *streamId = static_cast<Handle*>(handle)->stream;
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+// ---- workspace: tfqmrgpu.cu:682-698 -----------------------------------------------------------------
+tfqmrgpuStatus_t tfqmrgpuCreateWorkspace(void* *pBuffer, size_t const pBufferSizeInBytes, char const memType) {
+    if (nullptr == pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    cudaError_t const err = ('m' == lower(memType)) ? cudaMallocManaged(pBuffer, pBufferSizeInBytes)
+                                                    : cudaMalloc(pBuffer, pBufferSizeInBytes);
+    if (cudaSuccess != err) { cudaGetLastError(); return TFQ_ERR(TFQMRGPU_STATUS_ALLOCATION_FAILED); }
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+tfqmrgpuStatus_t tfqmrgpuDestroyWorkspace(void* pBuffer) {
+    return (cudaSuccess == cudaFree(pBuffer)) ? TFQMRGPU_STATUS_SUCCESS : TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+}
+
+// ---- block sizes: tfqmrgpu.cu:75-106 ----------------------------------------------------------------
+tfqmrgpuStatus_t tfqmrgpu_bsrsv_allowedBlockSizes(int32_t *number, int32_t *blockSizes, int const arrayLength) {
+    if (nullptr == number) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+    if (nullptr == blockSizes) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+    if (0 != *number) for (int i = 0; i < arrayLength; ++i) blockSizes[i] = 0; // tfqmrgpu.cu:83
+    int n = 0, written = 0;
+    for (auto const &bs : kAllowedBlockSizes) {
+        ++n;
+        if (2*n < arrayLength) { blockSizes[2*written] = bs[0]; blockSizes[2*written + 1] = bs[1]; ++written; } // tfqmrgpu.cu:88
+    }
+    *number = n;
+    return (n == written) ? TFQMRGPU_STATUS_SUCCESS : TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+}
+tfqmrgpuStatus_t tfqmrgpu_bsrsv_blockSizeMissing(int const ldA, int const ldB) {
+    if (block_size_allowed(ldA, ldB)) return TFQMRGPU_STATUS_SUCCESS;
+    return TFQMRGPU_BLOCKSIZE_MISSING + TFQMRGPU_CODE_CHAR*ldA + TFQMRGPU_CODE_LINE*ldB;
+}
+
+// ---- plan: tfqmrgpu.cu:136-361 ----------------------------------------------------------------------
+tfqmrgpuStatus_t tfqmrgpu_bsrsv_createPlan(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t *plan, int const mb,
+    int32_t const *bsrRowPtrA, int const nnzbA, int32_t const *bsrColIndA,
+    int32_t const *bsrRowPtrX, int const nnzbX, int32_t const *bsrColIndX,
+    int32_t const *bsrRowPtrB, int const nnzbB, int32_t const *bsrColIndB,
+    int const indexOffset, int const echo)
+{
+    if (nullptr == plan) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    if (nullptr != *plan) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);             // tfqmrgpu.cu:161
+    if (mb < 1) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);                    // tfqmrgpu.cu:166-172
+    if (nnzbX < 1) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+    if (nnzbB > nnzbX) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+    if (nnzbA < 0 || nnzbB < 0) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+    if ((long long)nnzbA > (long long)mb*mb) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+    if (!bsrRowPtrA || !bsrRowPtrX || !bsrRowPtrB) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    if ((nnzbA && !bsrColIndA) || !bsrColIndX || (nnzbB && !bsrColIndB)) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    if (nnzbA != bsrRowPtrA[mb] - bsrRowPtrA[0]) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+    if (nnzbX != bsrRowPtrX[mb] - bsrRowPtrX[0]) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+    if (nnzbB != bsrRowPtrB[mb] - bsrRowPtrB[0]) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+
+    Plan *p = new (std::nothrow) Plan();
+    if (nullptr == p) return TFQ_ERR(TFQMRGPU_STATUS_ALLOCATION_FAILED);
+    p->mb = mb; p->nnzbA = nnzbA; p->nnzbX = nnzbX; p->nnzbB = nnzbB; p->indexOffset = indexOffset;
+    cudaStream_t const stream = handle ? static_cast<Handle*>(handle)->stream : nullptr;
+    tfqmrgpuStatus_t const st = plan_analyse(*p, stream, bsrRowPtrA, bsrColIndA, bsrRowPtrX, bsrColIndX, bsrRowPtrB, bsrColIndB, echo);
+    if (TFQMRGPU_STATUS_SUCCESS != st) { plan_release(*p); delete p; return st; }
+    *plan = reinterpret_cast<tfqmrgpuBsrsvPlan_t>(p);
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+tfqmrgpuStatus_t tfqmrgpu_bsrsv_destroyPlan(tfqmrgpuHandle_t, tfqmrgpuBsrsvPlan_t plan) {
+    if (nullptr == plan) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    plan_release(*P(plan));
+    delete P(plan);
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+// ---- bufferSize: tfqmrgpu.cu:364-412 ----------------------------------------------------------------
+tfqmrgpuStatus_t tfqmrgpu_bsrsv_bufferSize(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan,
+    int const ldA, int const blockDim, int const ldB, int const RhsBlockDim, char const precision, size_t *pBufferSizeInBytes)
+{
+    int const LM = ldA, LN = ldB;
+    if (LM != blockDim) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+    if (LM > LN) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+    if (LN != RhsBlockDim) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+    if (nullptr == plan || nullptr == handle) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan &p = *P(plan);
+    char prec;
+    switch (lower(precision)) { // tfqmrgpu.cu:383-390
+        case 'f': case 'c': prec = 'c'; break;
+        case 'm': prec = 'm'; break;
+        case 'd': case 'z': prec = 'z'; break;
+        default: prec = 'z';
+    }
+    p.LM = LM; p.LN = LN; p.precision = prec;
+    if (nullptr == pBufferSizeInBytes) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    *pBufferSizeInBytes = 0;
+    if (!block_size_allowed(LM, LN)) return TFQMRGPU_BLOCKSIZE_MISSING + TFQMRGPU_CODE_CHAR*LM + TFQMRGPU_CODE_LINE*LN; // tfqmrgpu.cu:70
+    if ('m' == prec) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, prec);                                             // tfqmrgpu.cu:44
+    tfqmrgpuStatus_t const st = plan_configure(p, static_cast<Handle*>(handle)->stream, LM, LN, prec);
+    if (TFQMRGPU_STATUS_SUCCESS != st) return st;
+    p.pBuffer = nullptr; p.v3_ready = false; // a new size invalidates a previously registered buffer
+    *pBufferSizeInBytes = p.bufferBytes;
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+// ---- setBuffer / getBuffer: tfqmrgpu.cu:415-462 -----------------------------------------------------
+tfqmrgpuStatus_t tfqmrgpu_bsrsv_setBuffer(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, void* const pBuffer) {
+    if (nullptr == pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    if (nullptr == plan || nullptr == handle) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan &p = *P(plan);
+    if (0 == p.bufferBytes) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR); // bufferSize has not been called
+    if (size_t(pBuffer) & 255) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);  // 2^TFQMRGPU_MEMORY_ALIGNMENT
+    cudaStream_t const stream = static_cast<Handle*>(handle)->stream;
+    p.pBuffer = static_cast<char*>(pBuffer);
+    TFQ_CUDA(cudaMemsetAsync(p.pBuffer + p.off_zero, 0, p.bufferBytes - 256 - p.off_zero, stream)); // zero block, scalars, tickets, control
+    tfqmrgpuStatus_t const st = fill_v3(p, stream);
+    if (TFQMRGPU_STATUS_SUCCESS != st) return st;
+    p.v3_ready = true;
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+tfqmrgpuStatus_t tfqmrgpu_bsrsv_getBuffer(tfqmrgpuHandle_t, tfqmrgpuBsrsvPlan_t plan, void* *pBuffer) {
+    if (nullptr == plan || nullptr == pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    *pBuffer = P(plan)->pBuffer;
+    if (nullptr == *pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+// ---- setMatrix / getMatrix: tfqmrgpu.cu:467-645 -----------------------------------------------------
+tfqmrgpuStatus_t tfqmrgpu_bsrsv_setMatrix(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, char const var, void const *val,
+    char const precision, int const, int const, char const transposition, tfqmrgpuDataLayout_t const layout)
+{
+    bool trans = false; double scal_imag = 1;
+    tfqmrgpuStatus_t st = parse_layout_trans(layout, transposition, trans, scal_imag);
+    if (st) return st;
+    if (nullptr == plan || nullptr == handle) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan &p = *P(plan);
+    cudaStream_t const stream = static_cast<Handle*>(handle)->stream;
+    bool const is_double = ('z' == p.precision);
+    size_t const s = is_double ? 8 : 4;
+    char const v = lower(var);
+    uint32_t nnzb = 0;
+    switch (v) {
+        case 'a': nnzb = p.nnzbA; trans = !trans; break; // A is stored transposed [k][i] (tfqmrgpu.cu:509-520)
+        case 'b': nnzb = p.nnzbB; break;
+        case 'x': nnzb = p.nnzbX; break;
+        default: return TFQ_ERRC(TFQMRGPU_VARIABLENAME_UNKNOWN, var);
+    }
+    if (nnzb < 1) return TFQMRGPU_STATUS_SUCCESS;
+    if (nullptr == p.pBuffer || nullptr == val) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    if (('z' == lower(precision)) != is_double) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, precision); // tfqmrgpu.cu:538-542
+    if ('a' == v) {
+        char *const dst = p.pBuffer + p.off_A;
+        TFQ_CUDA(cudaMemcpyAsync(dst, val, size_t(nnzb)*2*p.LM*p.LM*s, cudaMemcpyHostToDevice, stream));
+        return convert_inplace(p, dst, nnzb, p.LM, p.LM, is_double, layout, trans, scal_imag, stream);
+    }
+    if ('b' == v) {
+        char *const dst = p.pBuffer + p.off_B;
+        TFQ_CUDA(cudaMemcpyAsync(dst, val, size_t(nnzb)*2*p.LM*p.LN*s, cudaMemcpyHostToDevice, stream));
+        return convert_inplace(p, dst, nnzb, p.LM, p.LN, is_double, layout, trans, scal_imag, stream);
+    }
+    // 'x': accepted like in the reference; note that solve() discards the initial guess (core.hxx:125)
+    char *const scratch = p.pBuffer + p.off_v[9];
+    TFQ_CUDA(cudaMemcpyAsync(scratch, val, p.vecBytes, cudaMemcpyHostToDevice, stream));
+    return convert_permuted(p, p.pBuffer + p.off_v[1], scratch, nnzb, p.LM, p.LN, is_double, layout, trans, scal_imag, true, stream);
+}
+
+tfqmrgpuStatus_t tfqmrgpu_bsrsv_getMatrix(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, char const var, void *val,
+    char const precision, int const, int const, char const transposition, tfqmrgpuDataLayout_t const layout)
+{
+    if ('x' != lower(var)) return TFQ_ERRC(TFQMRGPU_UNDOCUMENTED_ERROR, var); // only X can be downloaded (tfqmrgpu.cu:635-643)
+    if (nullptr == plan || nullptr == handle) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    return download_vector(static_cast<Handle*>(handle), *P(plan), P(plan)->off_v[1], val, precision, transposition, layout);
+}
+
+// ---- solve / getInfo: tfqmrgpu.cu:648-679 -----------------------------------------------------------
+tfqmrgpuStatus_t tfqmrgpu_bsrsv_solve(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, double const threshold, int const maxIterations) {
+    if (nullptr == plan || nullptr == handle) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    return solve(*P(plan), static_cast<Handle*>(handle)->stream, threshold, maxIterations);
+}
+
+tfqmrgpuStatus_t tfqmrgpu_bsrsv_getInfo(tfqmrgpuHandle_t, tfqmrgpuBsrsvPlan_t plan, double *residuum_reached,
+    int32_t *iterations_needed, double *flops_performed, double *flops_performed_all)
+{
+    if (nullptr == plan) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan const &p = *P(plan);
+    int any = 0;
+    if (residuum_reached)    { ++any; *residuum_reached    = p.residuum_reached; }
+    if (iterations_needed)   { ++any; *iterations_needed   = p.iterations_needed; }
+    if (flops_performed)     { ++any; *flops_performed     = p.flops_performed; }
+    if (flops_performed_all) { ++any; *flops_performed_all = p.flops_performed_all; }
+    return any ? TFQMRGPU_STATUS_SUCCESS : TFQMRGPU_STATUS_NO_INFO_PASSED;
+}
+
+} // extern "C"
+
+// ---- quick starters: tfqmrgpu.cu:702-821 ------------------------------------------------------------
+namespace tfq {
+template <typename real_t>
+static tfqmrgpuStatus_t one_shot(int mb, int ldA, int ldB,
+    int32_t const *rowPtrA, int nnzbA, int32_t const *colIndA, real_t const *Amat, char transA,
+    int32_t const *rowPtrX, int nnzbX, int32_t const *colIndX, real_t *Xmat, char transX,
+    int32_t const *rowPtrB, int nnzbB, int32_t const *colIndB, real_t const *Bmat, char transB,
+    int32_t *iterations, float *residual, int indexOffset, int echo)
+{
+    char const zoc = (8 == sizeof(real_t)) ? 'z' : 'c';
+    if (echo > 0) std::printf("# tfqmrgpu_bsrsv_%c: mb= %d, ldA= %d, ldB= %d, iterations= %d, residual= %.1e\n",
+                              zoc, mb, ldA, ldB, iterations ? *iterations : -1, residual ? double(*residual) : -1.);
+    tfqmrgpuHandle_t handle = nullptr;
+    tfqmrgpuBsrsvPlan_t plan = nullptr;
+    void *buffer = nullptr;
+    tfqmrgpuStatus_t stat = TFQMRGPU_STATUS_SUCCESS;
+    char const *where = "";
+    // unlike the reference, every exit path releases what was acquired
+#define STEP(name, call) if (TFQMRGPU_STATUS_SUCCESS == stat) { stat = (call); where = name; }
+    STEP("tfqmrgpuCreateHandle", tfqmrgpuCreateHandle(&handle))
+    STEP("tfqmrgpuSetStream", tfqmrgpuSetStream(handle, nullptr))
+    STEP("tfqmrgpu_bsrsv_createPlan", tfqmrgpu_bsrsv_createPlan(handle, &plan, mb, rowPtrA, nnzbA, colIndA, rowPtrX, nnzbX, colIndX,
+                                                                 rowPtrB, nnzbB, colIndB, indexOffset, echo))
+    size_t bytes = 0;
+    STEP("tfqmrgpu_bsrsv_bufferSize", tfqmrgpu_bsrsv_bufferSize(handle, plan, ldA, ldA, ldB, ldB, zoc, &bytes))
+    STEP("tfqmrgpuCreateWorkspace", tfqmrgpuCreateWorkspace(&buffer, bytes, 'd'))
+    STEP("tfqmrgpu_bsrsv_setBuffer", tfqmrgpu_bsrsv_setBuffer(handle, plan, buffer))
+    STEP("tfqmrgpu_bsrsv_setMatrix('A')", tfqmrgpu_bsrsv_setMatrix(handle, plan, 'A', Amat, zoc, ldA, ldA, transA, TFQMRGPU_LAYOUT_RIRIRIRI))
+    STEP("tfqmrgpu_bsrsv_setMatrix('B')", tfqmrgpu_bsrsv_setMatrix(handle, plan, 'B', Bmat, zoc, ldB, ldA, transB, TFQMRGPU_LAYOUT_RIRIRIRI))
+    double const threshold = residual ? double(*residual) : 1e-9;
+    int const maxiter = iterations ? *iterations : 200;
+    STEP("tfqmrgpu_bsrsv_solve", tfqmrgpu_bsrsv_solve(handle, plan, threshold, maxiter))
+    double residuum = 0, flops = 0, flops_all = 0;
+    int32_t needed = 0;
+    STEP("tfqmrgpu_bsrsv_getInfo", tfqmrgpu_bsrsv_getInfo(handle, plan, &residuum, &needed, &flops, &flops_all))
+    if (TFQMRGPU_STATUS_SUCCESS == stat) {
+        if (echo > 1) std::printf("# tfQMRgpu needed %d iterations to converge to %.1e using %g GFlop\n", needed, residuum, flops*1e-9);
+        if (residual) *residual = float(residuum);
+        if (iterations) *iterations = needed;
+    }
+    STEP("tfqmrgpu_bsrsv_getMatrix", tfqmrgpu_bsrsv_getMatrix(handle, plan, 'X', Xmat, zoc, ldB, ldA, transX, TFQMRGPU_LAYOUT_RIRIRIRI))
+#undef STEP
+    if (stat && echo > 0) std::printf("# tfqmrgpu_bsrsv_%c: %s returned %d\n", zoc, where, stat);
+    if (buffer) tfqmrgpuDestroyWorkspace(buffer);
+    if (plan) tfqmrgpu_bsrsv_destroyPlan(handle, plan);
+    if (handle) tfqmrgpuDestroyHandle(handle);
+    return stat;
+}
+} // namespace tfq
+
+extern "C" {
+
+tfqmrgpuStatus_t tfqmrgpu_bsrsv_z(int mb, int ldA, int ldB,
+    int32_t const* rowPtrA, int nnzbA, int32_t const* colIndA, double const* Amat, char transA,
+    int32_t const* rowPtrX, int nnzbX, int32_t const* colIndX, double* Xmat, char transX,
+    int32_t const* rowPtrB, int nnzbB, int32_t const* colIndB, double const* Bmat, char transB,
+    int32_t *iterations, float *residual, int indexOffset, int echo) {
+    return one_shot<double>(mb, ldA, ldB, rowPtrA, nnzbA, colIndA, Amat, transA, rowPtrX, nnzbX, colIndX, Xmat, transX,
+                            rowPtrB, nnzbB, colIndB, Bmat, transB, iterations, residual, indexOffset, echo);
+}
+tfqmrgpuStatus_t tfqmrgpu_bsrsv_c(int mb, int ldA, int ldB,
+    int32_t const* rowPtrA, int nnzbA, int32_t const* colIndA, float const* Amat, char transA,
+    int32_t const* rowPtrX, int nnzbX, int32_t const* colIndX, float* Xmat, char transX,
+    int32_t const* rowPtrB, int nnzbB, int32_t const* colIndB, float const* Bmat, char transB,
+    int32_t *iterations, float *residual, int indexOffset, int echo) {
+    return one_shot<float>(mb, ldA, ldB, rowPtrA, nnzbA, colIndA, Amat, transA, rowPtrX, nnzbX, colIndX, Xmat, transX,
+                           rowPtrB, nnzbB, colIndB, Bmat, transB, iterations, residual, indexOffset, echo);
+}
+
+// ---- extensions (tfqmrgpu_b200_ext.h) ---------------------------------------------------------------
+tfqmrgpuStatus_t tfqmrgpux_getVersion(int *major, int *minor, int *patch) {
+    if (major) *major = 0; if (minor) *minor = 1; if (patch) *patch = 0;
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+tfqmrgpuStatus_t tfqmrgpux_setVerbosity(int level) { set_verbosity(level); return TFQMRGPU_STATUS_SUCCESS; }
+
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getPlanArray(tfqmrgpuBsrsvPlan_t plan, int kind, void *out, size_t *count) {
+    if (nullptr == plan) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan const &p = *P(plan);
+    void const *src = nullptr; size_t n = 0, es = 4; bool host = false;
+    switch (kind) {
+        case 0: src = p.d_starts;  n = size_t(p.nnzbX) + 1; break;
+        case 1: src = p.d_pairs;   n = 2*size_t(p.nPairs); break;
+        case 2: src = p.d_subset;  n = size_t(p.nnzbB); break;
+        case 3: src = p.d_colindx; n = size_t(p.nnzbX); es = 2; break;
+        case 4: src = p.d_perm;    n = size_t(p.nnzbX); break;
+        case 5: src = p.h_colstart.data(); n = p.h_colstart.size(); host = true; break;
+        default: return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+    }
+    if (count) *count = n;
+    if (out && n) {
+        if (host) std::memcpy(out, src, n*es);
+        else TFQ_CUDA(cudaMemcpy(out, src, n*es, cudaMemcpyDeviceToHost));
+    }
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getPlanInfo(tfqmrgpuBsrsvPlan_t plan, int64_t info[16]) {
+    if (nullptr == plan || nullptr == info) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan const &p = *P(plan);
+    int64_t const v[16] = {p.nnzbX, p.nnzbB, p.nnzbA, int64_t(p.nCols), int64_t(p.nPairs), p.LM, p.LN, p.precision,
+                           int64_t(p.nTiles), int64_t(p.nUnits), int64_t(p.gmax), int64_t(p.nEntries), p.mb, 0, 0, 0};
+    std::memcpy(info, v, sizeof(v));
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setV3(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, float const *v3, int onDevice) {
+    if (nullptr == plan || nullptr == handle || nullptr == v3) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan &p = *P(plan);
+    if (nullptr == p.pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    cudaStream_t const stream = static_cast<Handle*>(handle)->stream;
+    size_t const bytes = size_t(p.nnzbX)*2*p.LM*p.LN*sizeof(float);
+    float *const scratch = ws<float>(p, p.off_v[9]);
+    TFQ_CUDA(cudaMemcpyAsync(scratch, v3, bytes, onDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+    tfqmrgpuStatus_t const st = permute_v3(p, ws<float>(p, p.off_v[3]), scratch, true, stream);
+    if (st) return st;
+    TFQ_CUDA(cudaStreamSynchronize(stream));
+    p.v3_ready = true;
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getV3(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, float *v3Host) {
+    if (nullptr == plan || nullptr == handle || nullptr == v3Host) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan &p = *P(plan);
+    if (nullptr == p.pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    cudaStream_t const stream = static_cast<Handle*>(handle)->stream;
+    float *const scratch = ws<float>(p, p.off_v[9]);
+    tfqmrgpuStatus_t const st = permute_v3(p, scratch, ws<float const>(p, p.off_v[3]), false, stream);
+    if (st) return st;
+    TFQ_CUDA(cudaMemcpyAsync(v3Host, scratch, size_t(p.nnzbX)*2*p.LM*p.LN*sizeof(float), cudaMemcpyDeviceToHost, stream));
+    TFQ_CUDA(cudaStreamSynchronize(stream));
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_multiply(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, int nrep) {
+    if (nullptr == plan || nullptr == handle) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan &p = *P(plan);
+    if (nullptr == p.pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    for (int r = 0; r < nrep; ++r) {
+        tfqmrgpuStatus_t const st = launch_spmm(p, p.pBuffer + p.off_v[9], p.pBuffer + p.off_v[1], -1, static_cast<Handle*>(handle)->stream);
+        if (st) return st;
+    }
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getVector(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, char var, void *val,
+    char precision, char trans, tfqmrgpuDataLayout_t layout) {
+    if (nullptr == plan || nullptr == handle) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan &p = *P(plan);
+    size_t off;
+    switch (lower(var)) {
+        case 'x': off = p.off_v[1]; break;
+        case 'y': off = p.off_v[9]; break;
+        default: return TFQ_ERRC(TFQMRGPU_VARIABLENAME_UNKNOWN, var);
+    }
+    return download_vector(static_cast<Handle*>(handle), p, off, val, precision, trans, layout);
+}
+
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getWindow(tfqmrgpuBsrsvPlan_t plan, char var, size_t *offset, size_t *length) {
+    if (nullptr == plan || nullptr == offset || nullptr == length) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan const &p = *P(plan);
+    size_t const s = ('z' == p.precision) ? 8 : 4;
+    switch (lower(var)) {
+        case 'x': *offset = p.off_v[1]; *length = p.vecBytes; break;
+        case 'y': *offset = p.off_v[9]; *length = p.vecBytes; break;
+        case '3': *offset = p.off_v[3]; *length = size_t(p.nnzbX)*2*p.LM*p.LN*4; break;
+        case 'a': *offset = p.off_A; *length = size_t(p.nnzbA)*2*p.LM*p.LM*s; break;
+        case 'b': *offset = p.off_B; *length = size_t(p.nnzbB)*2*p.LM*p.LN*s; break;
+        default: return TFQ_ERRC(TFQMRGPU_VARIABLENAME_UNKNOWN, var);
+    }
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getRhsStatus(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, int8_t *statusHost) {
+    if (nullptr == plan || nullptr == handle || nullptr == statusHost) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan const &p = *P(plan);
+    if (nullptr == p.pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    cudaStream_t const stream = static_cast<Handle*>(handle)->stream;
+    TFQ_CUDA(cudaMemcpyAsync(statusHost, p.pBuffer + p.off_status, size_t(p.nCols)*p.LN, cudaMemcpyDeviceToHost, stream));
+    TFQ_CUDA(cudaStreamSynchronize(stream));
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getSolveStats(tfqmrgpuBsrsvPlan_t plan, double stats[8]) {
+    if (nullptr == plan || nullptr == stats) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan const &p = *P(plan);
+    stats[0] = p.stat_probes; stats[1] = p.stat_launches; stats[2] = p.stat_bodies; stats[3] = p.stat_ms;
+    stats[4] = p.stat_bound2; stats[5] = p.stat_target2; stats[6] = 0; stats[7] = 0;
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+} // extern "C"

@@ -1,0 +1,119 @@
+// The tfQMR iteration driver.
+//
+// Role of tfqmrgpu::solve (tfqmrgpu_core.hxx:20-335).  The reference decides on the HOST after every
+// iteration (two blocking device->host copies of tau and status, core.hxx:235-236) whether to probe
+// the true residual.  Here the solver state lives on the device (tfq::Control): the last CTA of the
+// last kernel of an iteration evaluates the reference's rule and sets state = RUN | PROBE | DONE, and
+// every kernel starts by checking that state.  The host therefore only ENQUEUES iteration bodies
+// (iteration kernels followed by the probe kernels, which are no-ops unless state == PROBE) and looks
+// at an asynchronous read-back of the control block a few bodies behind, so host and device never
+// serialise inside the loop while the iteration/probe sequence stays exactly the reference's.
+#include "tfq_internal.hpp"
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+namespace tfq {
+
+namespace {
+constexpr int kAhead = 3;      // iteration bodies the host may run ahead of the last control read-back
+constexpr int kRing = 6;       // read-back slots; slot 6 = final state, slot 7 = upload staging
+}
+
+tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIterations)
+{
+    auto const t_start = std::chrono::steady_clock::now();
+    // block size / precision dispatch of the reference (tfqmrgpu.cu:40-72)
+    if (!block_size_allowed(p.LM, p.LN))
+        return TFQMRGPU_BLOCKSIZE_MISSING + TFQMRGPU_CODE_CHAR*p.LM + TFQMRGPU_CODE_LINE*p.LN;
+    if ('z' != p.precision && 'c' != p.precision) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, p.precision);
+    if (nullptr == p.pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+
+    if (nullptr == p.h_ctl) {
+        TFQ_CUDA(cudaMallocHost((void**)&p.h_ctl, 8*sizeof(Control)));
+        for (auto &e : p.ev) TFQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    Control *const d_ctl = ws<Control>(p, p.off_ctl);
+    double launches = 0;
+
+    // ---- initial state (core.hxx:114-131,170-174) ----------------------------------------------------
+    Control &c0 = p.h_ctl[7];
+    std::memset(&c0, 0, sizeof(Control));
+    c0.state = (maxIterations > 0) ? STATE_RUN : STATE_DONE;
+    c0.max_iterations = maxIterations;
+    c0.result = TFQMRGPU_STATUS_MAX_ITERATIONS;
+    c0.iterations_needed = maxIterations;
+    c0.tol2 = tolerance*tolerance;
+    c0.target_bound2 = c0.tol2*100*100;
+    c0.residual2_reached = 1e300;
+    TFQ_CUDA(cudaMemcpyAsync(d_ctl, &c0, sizeof(Control), cudaMemcpyHostToDevice, stream));
+    TFQ_CUDA(cudaMemsetAsync(p.pBuffer + p.off_ticket, 0, (size_t(p.nCols) + 8)*4, stream));
+    // v1 and v4..v9 are contiguous: the initial guess is discarded like in the reference (core.hxx:125)
+    TFQ_CUDA(cudaMemsetAsync(p.pBuffer + p.off_v[1], 0, (p.off_v[9] + p.vecBytes) - p.off_v[1], stream));
+
+    tfqmrgpuStatus_t st;
+#define TFQ_DO(call) do { st = (call); if (TFQMRGPU_STATUS_SUCCESS != st) return st; launches += 1; } while (0)
+    TFQ_DO(launch_add_rhs(p, p.pBuffer + p.off_v[5], 1.0, -1, stream));    // v5 := b        (core.hxx:153)
+    TFQ_DO(launch_vecop(p, OP_INIT, stream));                              // tau, 1/|b|^2, first dec35
+
+    if (verbosity() > 0) { // the reference prints this line unconditionally (core.hxx:167)
+        std::vector<double> inv(size_t(p.nCols)*p.LN);
+        TFQ_CUDA(cudaMemcpyAsync(inv.data(), p.pBuffer + p.off_invBn2, inv.size()*8, cudaMemcpyDeviceToHost, stream));
+        TFQ_CUDA(cudaStreamSynchronize(stream));
+        double mn = 9e99, mx = -1;
+        for (double v : inv) { double const n2 = 1./v; mn = std::min(mn, n2); mx = std::max(mx, n2); }
+        std::printf("# norms of B within [%g, %g]\n", std::sqrt(mn), std::sqrt(mx));
+    }
+
+    void *const v1 = p.pBuffer + p.off_v[1], *const v6 = p.pBuffer + p.off_v[6];
+    void *const v8 = p.pBuffer + p.off_v[8], *const v9 = p.pBuffer + p.off_v[9];
+
+    int bodies = 0;
+    for (int i = 0; i < maxIterations; ++i) {
+        if (i >= kAhead) {
+            int const slot = (i - kAhead) % kRing;
+            TFQ_CUDA(cudaEventSynchronize(p.ev[slot]));
+            if (STATE_DONE == p.h_ctl[slot].state) break;
+        }
+        // ---- one tfQMR iteration (core.hxx:189-233); all kernels are no-ops unless state == RUN ------
+        TFQ_DO(launch_vecop(p, OP_K1, stream));
+        TFQ_DO(launch_spmm(p, v9, v6, STATE_RUN, stream));                 // v9 := A*v6     (core.hxx:198)
+        TFQ_DO(launch_vecop(p, OP_E1, stream));
+        TFQ_DO(launch_vecop(p, OP_K2, stream));
+        TFQ_DO(launch_vecop(p, OP_K3, stream));
+        TFQ_DO(launch_spmm(p, v8, v6, STATE_RUN, stream));                 // v8 := A*v6     (core.hxx:224)
+        TFQ_DO(launch_vecop(p, OP_E2, stream));
+        TFQ_DO(launch_vecop(p, OP_K4, stream));
+        // ---- residual probe (core.hxx:263-304); no-ops unless the device asked for it ---------------
+        TFQ_DO(launch_spmm(p, v9, v1, STATE_PROBE, stream));               // v9 := A*v1     (core.hxx:265)
+        TFQ_DO(launch_add_rhs(p, v9, -1.0, STATE_PROBE, stream));          // v9 -= b        (core.hxx:267)
+        TFQ_DO(launch_vecop(p, OP_N3, stream));
+        int const slot = i % kRing;
+        TFQ_CUDA(cudaMemcpyAsync(&p.h_ctl[slot], d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, stream));
+        TFQ_CUDA(cudaEventRecord(p.ev[slot], stream));
+        ++bodies;
+    }
+#undef TFQ_DO
+    Control &fin = p.h_ctl[6];
+    TFQ_CUDA(cudaMemcpyAsync(&fin, d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, stream));
+    TFQ_CUDA(cudaStreamSynchronize(stream));
+    TFQ_CUDA(cudaGetLastError());
+
+    // ---- bookkeeping (core.hxx:133-138,324-325; flop formula of SURVEY.md a14) ------------------------
+    double const N = double(p.nnzbX)*p.LM*p.LN;
+    double const M = double(p.nPairs)*8.*p.LM*p.LM*p.LN;
+    p.flops_performed = fin.iteration*(104.*N + 2.*M) + 4.*N + fin.probes*(M + 4.*N);
+    p.flops_performed_all += p.flops_performed; // the reference never accumulates this (defect, fixed)
+    p.residuum_reached = std::sqrt(fin.residual2_reached);
+    p.iterations_needed = fin.iterations_needed;
+    p.solved = true;
+    p.stat_probes = fin.probes; p.stat_launches = launches; p.stat_bodies = bodies;
+    p.stat_bound2 = fin.max_bound2; p.stat_target2 = fin.target_bound2;
+    p.stat_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+    if (verbosity() > 1)
+        std::printf("# tfQMRgpu(B200): %d iterations, %d probes, residual %.3e, status %d, %.3f ms\n",
+                    fin.iteration, fin.probes, p.residuum_reached, fin.result, p.stat_ms);
+    return fin.result;
+}
+
+} // namespace tfq

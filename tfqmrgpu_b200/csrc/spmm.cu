@@ -1,0 +1,259 @@
+// Block-sparse product  Y = A * X  over complex LM x LM A-blocks and LM x LN X-blocks.
+//
+// Role of the reference's blocksparse_action_t::multiply + gemmNxNf (tfqmrgpu_blocksparse.hxx:71-199,
+// tfqmrgpu_blockmult.hxx:10-93), re-designed for sm_100a:
+//   * one CTA per "unit" = one block row of A times up to gmax of that row's block columns, so every
+//     A block is fetched ONCE per unit and reused across all its right-hand-side columns (the
+//     reference re-reads A for every Y block);
+//   * A and X k-slabs are staged in shared memory by the bulk-copy engine (cp.async.bulk, i.e. TMA
+//     without a tensor map; SASS: UBLKCP) into a 3-stage ring completed through mbarriers, so copy and
+//     FMA work overlap and there are no per-k __syncthreads (the reference has two per k);
+//   * each thread owns a TI x TJ register tile of complex accumulators and reads its operands with
+//     128-bit shared-memory loads (A broadcast across the j-threads, X conflict-free).
+// Internal layouts: A[nnzbA][2][LM(k)][LM(i)] (transposed), X,Y[nnzb][2][LM][LN] in storage order.
+// Arithmetic: accumulators in real_t over all pairs and k like blockmult.hxx:28-82.
+#include "tfq_internal.hpp"
+#include <type_traits>
+
+namespace tfq {
+
+namespace {
+
+constexpr int kStages = 3;
+
+template <typename real_t> struct SpmmArgs {
+    real_t *y; real_t const *x; real_t const *A; real_t const *zero;
+    uint32_t const *unit_e0, *unit_y, *ent_a, *ent_x;
+    Control const *ctl; int expect;
+    int gmax, kc;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(void const *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (bytes: multiple of 16, 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, void const *src_gmem, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <typename T, int N>
+__device__ __forceinline__ void load_vec(T (&r)[N], T const *p) {
+    if constexpr ((sizeof(T)*N) % 16 == 0) {
+        #pragma unroll
+        for (int q = 0; q < int(sizeof(T)*N/16); ++q) {
+            float4 const v = reinterpret_cast<float4 const*>(p)[q];
+            reinterpret_cast<float4*>(r)[q] = v;
+        }
+    } else if constexpr ((sizeof(T)*N) % 8 == 0) {
+        #pragma unroll
+        for (int q = 0; q < int(sizeof(T)*N/8); ++q) {
+            float2 const v = reinterpret_cast<float2 const*>(p)[q];
+            reinterpret_cast<float2*>(r)[q] = v;
+        }
+    } else {
+        #pragma unroll
+        for (int q = 0; q < N; ++q) r[q] = p[q];
+    }
+}
+template <typename T, int N>
+__device__ __forceinline__ void store_vec(T *p, T const (&r)[N]) {
+    if constexpr ((sizeof(T)*N) % 16 == 0) {
+        #pragma unroll
+        for (int q = 0; q < int(sizeof(T)*N/16); ++q) reinterpret_cast<float4*>(p)[q] = reinterpret_cast<float4 const*>(r)[q];
+    } else if constexpr ((sizeof(T)*N) % 8 == 0) {
+        #pragma unroll
+        for (int q = 0; q < int(sizeof(T)*N/8); ++q) reinterpret_cast<float2*>(p)[q] = reinterpret_cast<float2 const*>(r)[q];
+    } else {
+        #pragma unroll
+        for (int q = 0; q < N; ++q) p[q] = r[q];
+    }
+}
+
+template <typename real_t, int LM, int LN, int TI, int TJ>
+__global__ void __launch_bounds__(256)
+spmm_unit_kernel(SpmmArgs<real_t> const a)
+{
+    if (a.expect >= 0 && a.ctl->state != a.expect) return; // device-resident solver control
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *const bars = reinterpret_cast<uint64_t*>(smem_raw);
+    real_t *const stage0 = reinterpret_cast<real_t*>(smem_raw + 128);
+    __shared__ uint32_t s_y[16];
+    __shared__ int s_ng;
+
+    int const G = a.gmax, KC = a.kc;
+    int const CH = LM/KC;                            // k-chunks per entry
+    int const stageElems = 2*KC*(LM + G*LN);         // [A re][A im][g: X re, X im]
+    uint32_t const u = blockIdx.x;
+    uint32_t const e0 = a.unit_e0[u];
+    int const nE = int(a.unit_e0[u + 1] - e0);
+    int const nSteps = nE*CH;
+
+    int const tid = threadIdx.x;
+    int const NTJ = (G*LN)/TJ;
+    int const tj = tid % NTJ, ti = tid / NTJ;
+    int const g = (tj*TJ)/LN, j0 = (tj*TJ) % LN, i0 = ti*TI;
+
+    if (tid < 16) s_y[tid] = (tid < G) ? a.unit_y[size_t(u)*G + tid] : kNoBlock;
+    if (0 == tid) {
+        #pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (0 == tid) { int n = 0; for (int q = 0; q < G; ++q) n += (s_y[q] != kNoBlock); s_ng = n; }
+    __syncthreads();
+    int const ng = s_ng;
+    bool const active = (ti < LM/TI) && (g < ng);
+
+    // producer: warp 0 issues the bulk copies of one pipeline step
+    auto issue = [&](int st) {
+        int const s = st % kStages;
+        int const e = st / CH, ch = st - e*CH;
+        real_t *const dst = stage0 + size_t(s)*stageElems;
+        uint32_t const ia = a.ent_a[e0 + e];
+        int const lane = tid;
+        if (0 == lane) mbar_expect_tx(&bars[s], unsigned(2*KC*(LM + ng*LN)*sizeof(real_t)));
+        __syncwarp();
+        for (int c = lane; c < 2 + 2*ng; c += 32) {
+            if (c < 2) {
+                real_t const *src = a.A + (size_t(ia)*2 + c)*LM*LM + size_t(ch)*KC*LM;
+                bulk_g2s(dst + c*KC*LM, src, unsigned(KC*LM*sizeof(real_t)), &bars[s]);
+            } else {
+                int const gg = (c - 2) >> 1, ri = (c - 2) & 1;
+                uint32_t const ix = a.ent_x[size_t(e0 + e)*G + gg];
+                real_t const *base = (kNoBlock == ix) ? a.zero : a.x + size_t(ix)*2*LM*LN;
+                real_t const *src = base + size_t(ri)*LM*LN + size_t(ch)*KC*LN;
+                bulk_g2s(dst + 2*KC*LM + (gg*2 + ri)*KC*LN, src, unsigned(KC*LN*sizeof(real_t)), &bars[s]);
+            }
+        }
+    };
+
+    real_t acc_re[TI][TJ], acc_im[TI][TJ];
+    #pragma unroll
+    for (int ii = 0; ii < TI; ++ii) {
+        #pragma unroll
+        for (int jj = 0; jj < TJ; ++jj) { acc_re[ii][jj] = 0; acc_im[ii][jj] = 0; }
+    }
+
+    if (tid < 32) {
+        for (int st = 0; st < kStages - 1 && st < nSteps; ++st) issue(st);
+    }
+
+    for (int st = 0; st < nSteps; ++st) {
+        int const s = st % kStages;
+        if (tid < 32 && st + kStages - 1 < nSteps) issue(st + kStages - 1); // the slot was drained at the end of step st-1
+        if (active) {
+            mbar_wait(&bars[s], unsigned((st/kStages) & 1));
+            real_t const *const As_re = stage0 + size_t(s)*stageElems;
+            real_t const *const As_im = As_re + KC*LM;
+            real_t const *const Xs_re = As_re + 2*KC*LM + (g*2)*KC*LN;
+            real_t const *const Xs_im = Xs_re + KC*LN;
+            #pragma unroll 4
+            for (int kk = 0; kk < KC; ++kk) {
+                real_t ar[TI], ai[TI], xr[TJ], xi[TJ];
+                load_vec<real_t, TI>(ar, As_re + kk*LM + i0);
+                load_vec<real_t, TI>(ai, As_im + kk*LM + i0);
+                load_vec<real_t, TJ>(xr, Xs_re + kk*LN + j0);
+                load_vec<real_t, TJ>(xi, Xs_im + kk*LN + j0);
+                #pragma unroll
+                for (int ii = 0; ii < TI; ++ii) {
+                    #pragma unroll
+                    for (int jj = 0; jj < TJ; ++jj) {
+                        // complex multiply-accumulate, 8 flop (blockmult.hxx:76-77)
+                        acc_re[ii][jj] = fma( ar[ii], xr[jj], acc_re[ii][jj]);
+                        acc_re[ii][jj] = fma(-ai[ii], xi[jj], acc_re[ii][jj]);
+                        acc_im[ii][jj] = fma( ar[ii], xi[jj], acc_im[ii][jj]);
+                        acc_im[ii][jj] = fma( ai[ii], xr[jj], acc_im[ii][jj]);
+                    }
+                }
+            }
+        }
+        __syncthreads(); // everyone is done with stage s before it is refilled
+    }
+
+    if (active) {
+        uint32_t const iy = s_y[g];
+        real_t *const yre = a.y + size_t(iy)*2*LM*LN;
+        real_t *const yim = yre + LM*LN;
+        #pragma unroll
+        for (int ii = 0; ii < TI; ++ii) {
+            store_vec<real_t, TJ>(yre + (i0 + ii)*LN + j0, acc_re[ii]);
+            store_vec<real_t, TJ>(yim + (i0 + ii)*LN + j0, acc_im[ii]);
+        }
+    }
+}
+
+template <typename real_t, int LM, int LN>
+tfqmrgpuStatus_t launch_typed(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream)
+{
+    constexpr bool is_double = std::is_same<real_t, double>::value;
+    constexpr int TI = spmm_ti(is_double, LM, LN);
+    constexpr int TJ = spmm_tj(is_double, LN);
+    int const G = int(p.gmax);
+    // k-chunk: largest power-of-two slab with a stage of at most 24 KiB
+    int kc = LM;
+    while (kc > 4 && 2*size_t(kc)*(LM + size_t(G)*LN)*sizeof(real_t) > 24*1024) kc >>= 1;
+    size_t const stageBytes = 2*size_t(kc)*(LM + size_t(G)*LN)*sizeof(real_t);
+    size_t const smem = 128 + kStages*stageBytes;
+    int threads = (LM/TI)*((G*LN)/TJ);
+    threads = ((threads + 31)/32)*32;
+    if (threads > 256) return TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED);
+
+    auto kernel = spmm_unit_kernel<real_t, LM, LN, TI, TJ>;
+    static size_t configured = 0; // per instantiation
+    if (smem > configured) {
+        TFQ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured = smem;
+    }
+    SpmmArgs<real_t> a;
+    a.y = static_cast<real_t*>(y); a.x = static_cast<real_t const*>(x);
+    a.A = ws<real_t const>(p, p.off_A); a.zero = ws<real_t const>(p, p.off_zero);
+    a.unit_e0 = p.d_unit_e0; a.unit_y = p.d_unit_y; a.ent_a = p.d_ent_a; a.ent_x = p.d_ent_x;
+    a.ctl = ws<Control const>(p, p.off_ctl); a.expect = expect;
+    a.gmax = G; a.kc = kc;
+    if (p.nUnits > 0) kernel<<<p.nUnits, threads, smem, stream>>>(a);
+    TFQ_CUDA(cudaGetLastError());
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+template <int LM, int LN>
+tfqmrgpuStatus_t launch_sized(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream) {
+    if ('z' == p.precision) return launch_typed<double, LM, LN>(p, y, x, expect, stream);
+    if ('c' == p.precision) return launch_typed<float,  LM, LN>(p, y, x, expect, stream);
+    return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, p.precision); // 'm' is not implemented (tfqmrgpu.cu:42-44)
+}
+
+} // namespace
+
+tfqmrgpuStatus_t launch_spmm(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream)
+{
+    switch (p.LM*1000 + p.LN) {
+#define TFQ_CASE(LM, LN) case LM*1000 + LN: return launch_sized<LM, LN>(p, y, x, expect, stream);
+        TFQ_CASE( 4,  4) TFQ_CASE( 4,  5) TFQ_CASE( 4,  8) TFQ_CASE( 4, 32)
+        TFQ_CASE( 8,  8) TFQ_CASE( 8,  9) TFQ_CASE( 8, 10) TFQ_CASE( 8, 32) TFQ_CASE( 8, 64)
+        TFQ_CASE(16, 16) TFQ_CASE(16, 32) TFQ_CASE(16, 64)
+        TFQ_CASE(32, 32) TFQ_CASE(32, 64)
+        TFQ_CASE(64, 64)
+#undef TFQ_CASE
+        default: return TFQMRGPU_BLOCKSIZE_MISSING + TFQMRGPU_CODE_CHAR*p.LM + TFQMRGPU_CODE_LINE*p.LN; // tfqmrgpu.cu:70
+    }
+}
+
+} // namespace tfq

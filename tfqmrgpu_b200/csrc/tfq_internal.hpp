@@ -1,0 +1,144 @@
+// Internal declarations of the B200-native tfQMR library (not installed).
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <cstdio>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "../../include/tfqmrgpu_b200_ext.h"
+
+namespace tfq {
+
+// ---- error helpers -------------------------------------------------------------------------------
+inline tfqmrgpuStatus_t err_line(tfqmrgpuStatus_t code, int line) { return code + TFQMRGPU_CODE_LINE*(line % 10000); }
+inline tfqmrgpuStatus_t err_char(tfqmrgpuStatus_t code, char c, int line) {
+    return code + TFQMRGPU_CODE_CHAR*int((unsigned char)c) + TFQMRGPU_CODE_LINE*(line % 10000);
+}
+#define TFQ_ERR(code)        ::tfq::err_line(code, __LINE__)
+#define TFQ_ERRC(code, ch)   ::tfq::err_char(code, ch, __LINE__)
+// CUDA runtime failure -> LAUNCH_FAILED with the source line; never exits the process
+#define TFQ_CUDA(call) do { cudaError_t e_ = (call); if (cudaSuccess != e_) { \
+        if (::tfq::verbosity() > 0) std::fprintf(stderr, "tfQMRgpu: CUDA error \"%s\" at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+        return TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED); } } while (0)
+
+int  verbosity();
+void set_verbosity(int level);
+
+constexpr uint32_t kNoBlock = 0xffffffffu;   // "no such block" in SpMM entry tables
+constexpr int      kPartD   = 4;             // doubles per (tile, j) in the partial-sum scratch
+
+// ---- device-resident solver control (one per plan, lives in the workspace) ------------------------
+enum : int { STATE_RUN = 0, STATE_PROBE = 1, STATE_DONE = 2 };
+struct Control {
+    int      state;              // STATE_*
+    int      iteration;          // completed tfQMR iterations (core.hxx:180)
+    int      max_iterations;
+    int      probes;             // residual probes executed (core.hxx:263)
+    int      result;             // 0 converged, 9 max iterations, 6 breakdown (core.hxx:170,258,297)
+    int      iterations_needed;  // core.hxx:171,295
+    unsigned cols_done;          // ticket of the cross-column finalisation
+    int      pad_;
+    double   tol2;               // core.hxx:129
+    double   target_bound2;      // core.hxx:130,290
+    double   residual2_reached;  // core.hxx:131,287
+    double   max_bound2;         // core.hxx:252
+    double   min_norm2, max_norm2; // extrema of |b|^2 (core.hxx:161-167)
+};
+
+struct Handle { cudaStream_t stream = nullptr; };
+
+// one tile of the column-sorted vectors: blocks [b0, b1) all belong to block column `col`
+struct Tile { uint32_t col, b0, b1, pad; };
+
+struct Plan {
+    // ---- problem sizes -------------------------------------------------------------------------
+    int mb = 0, nnzbA = 0, nnzbX = 0, nnzbB = 0, indexOffset = 0;
+    uint32_t nCols = 0;
+    uint64_t nPairs = 0;
+    int LM = 0, LN = 0;
+    char precision = 0;               // 'c' | 'z' | 'm' once bufferSize has been called
+    int  maxColsPerRow = 1;
+
+    // ---- device index lists owned by the plan (cudaMalloc) -------------------------------------
+    // reference-format lists (tfqmrgpu_plan.hxx:20-50), built on the device
+    uint32_t *d_starts = nullptr, *d_pairs = nullptr, *d_subset = nullptr;
+    uint16_t *d_colindx = nullptr;
+    // column-sorted storage order of X-shaped vectors
+    uint32_t *d_perm = nullptr;       // caller X index -> storage index
+    uint32_t *d_iperm = nullptr;      // storage index -> caller X index
+    uint32_t *d_bpos = nullptr;       // storage index of the X block under each B block
+    std::vector<uint32_t> h_colstart; // [nCols+1] first storage block of every block column
+    std::vector<int32_t>  h_rowptrX;  // zero-based copy of bsrRowPtrX
+    // block-size dependent: vector tiles
+    Tile     *d_tiles = nullptr;      uint32_t nTiles = 0;
+    uint32_t *d_coltile = nullptr;    // [nCols+1] first tile of every block column
+    // block-size dependent: SpMM units (one CTA each): a block row times <= gmax block columns
+    uint32_t nUnits = 0, gmax = 1; uint64_t nEntries = 0;
+    uint32_t *d_unit_e0 = nullptr;    // [nUnits+1] first entry of every unit
+    uint32_t *d_unit_y = nullptr;     // [nUnits*gmax] storage index of the unit's Y blocks (kNoBlock = none)
+    uint32_t *d_ent_a = nullptr;      // [nEntries] A block of the entry
+    uint32_t *d_ent_x = nullptr;      // [nEntries*gmax] storage index of X blocks (kNoBlock = structural zero)
+
+    // ---- caller-owned workspace ------------------------------------------------------------------
+    char  *pBuffer = nullptr;
+    size_t bufferBytes = 0;
+    // byte offsets inside the workspace
+    size_t off_v[10] = {0};           // off_v[1], [3..9]: v1 (X), v3 (float), v4..v9
+    size_t off_B = 0, off_A = 0, off_zero = 0;
+    size_t off_rho = 0, off_alfa = 0, off_beta = 0, off_c67 = 0, off_eta = 0;
+    size_t off_tau = 0, off_var = 0, off_invBn2 = 0, off_status = 0, off_snap = 0;
+    size_t off_part = 0, off_colmon = 0, off_ticket = 0, off_ctl = 0;
+    size_t vecBytes = 0;              // bytes of one X-shaped vector
+
+    // ---- host side ---------------------------------------------------------------------------
+    Control *h_ctl = nullptr;         // pinned ring for control read-backs
+    cudaEvent_t ev[8] = {nullptr};
+    bool v3_ready = false, solved = false;
+
+    // ---- stats (tfqmrgpu_plan.hxx:41-45) -------------------------------------------------------
+    double residuum_reached = 0, flops_performed = -1, flops_performed_all = 0;
+    int    iterations_needed = -1;
+    double stat_probes = 0, stat_launches = 0, stat_bodies = 0, stat_ms = 0, stat_bound2 = 0, stat_target2 = 0;
+};
+
+// ---- plan analysis (plan.cu) ---------------------------------------------------------------------
+tfqmrgpuStatus_t plan_analyse(Plan &p, cudaStream_t stream,
+    int32_t const *rpA, int32_t const *ciA, int32_t const *rpX, int32_t const *ciX,
+    int32_t const *rpB, int32_t const *ciB, int echo);
+tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, char precision); // tiles, units, offsets
+void plan_release(Plan &p);
+
+// ---- kernels' host launchers --------------------------------------------------------------------
+// block-sparse product y = A*x on storage-ordered vectors; gate: run only if ctl->state == expect (expect < 0: always)
+tfqmrgpuStatus_t launch_spmm(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream);
+// fused vector algebra, see vecops.cu
+enum VecOp : int { OP_INIT = 0, OP_K1, OP_E1, OP_K2, OP_K3, OP_E2, OP_K4, OP_N3, OP_COUNT };
+tfqmrgpuStatus_t launch_vecop(Plan const &p, int op, cudaStream_t stream);
+// v[bpos[b]] += scal * B[b]   (linalg.hxx:383-428)
+tfqmrgpuStatus_t launch_add_rhs(Plan const &p, void *v, double scal, int expect, cudaStream_t stream);
+// host layout <-> internal layout (layout.cu)
+tfqmrgpuStatus_t convert_inplace(Plan const &p, void *blocks, uint32_t nnzb, int rows, int cols, bool is_double,
+                                 int layout, bool trans, double scal_imag, cudaStream_t stream);
+tfqmrgpuStatus_t convert_permuted(Plan const &p, void *dst, void const *src, uint32_t nnzb, int rows, int cols,
+                                  bool is_double, int layout, bool trans, double scal_imag, bool to_internal,
+                                  cudaStream_t stream);
+tfqmrgpuStatus_t permute_v3(Plan const &p, float *dst_storage, float const *src_caller, bool to_storage, cudaStream_t stream);
+
+// ---- solver driver (solver.cu) --------------------------------------------------------------------
+tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIterations);
+
+// register tile of the SpMM kernel (shared by plan.cu's unit builder and spmm.cu)
+constexpr int spmm_tj(bool is_double, int LN) {
+    return (LN % 4 == 0) ? (is_double ? 2 : 4) : ((LN % 2 == 0) ? 2 : 1);
+}
+constexpr int spmm_ti(bool is_double, int LM, int LN) {
+    return ((LM/4)*(LN/spmm_tj(is_double, LN)) > 256) ? 8 : 4;
+}
+
+bool block_size_allowed(int lm, int ln);
+extern const int kAllowedBlockSizes[15][2];
+
+template <typename T> inline T* ws(Plan const &p, size_t off) { return reinterpret_cast<T*>(p.pBuffer + off); }
+
+} // namespace tfq
