@@ -40,6 +40,10 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getPlanInfo(tfqmrgpuBsrsvPlan_t plan, int64_t i
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_setV3(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, float const *v3, int onDevice);
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_getV3(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, float *v3Host);
 
+/* The reference's shadow-vector stream (cuRAND XORWOW, seed 1234, linalg.hxx:784-797): n uniform floats
+ * written to DEVICE memory.  A column-sharded multi-GPU run slices the 1-GPU stream with this. */
+tfqmrgpuStatus_t tfqmrgpux_randomShadow(tfqmrgpuHandle_t handle, float *devOut, size_t n);
+
 /* Y := A*X on the plan's vectors (X = what setMatrix('X') uploaded or the last solution),
  * repeated nrep times on the handle's stream; asynchronous.  Fetch with getVector('Y'). */
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_multiply(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, int nrep);

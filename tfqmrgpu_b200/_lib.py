@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
 EXT_SYMBOLS = [
     "tfqmrgpux_getVersion", "tfqmrgpux_setVerbosity", "tfqmrgpux_bsrsv_getPlanArray", "tfqmrgpux_bsrsv_getPlanInfo",
     "tfqmrgpux_bsrsv_setV3", "tfqmrgpux_bsrsv_getV3", "tfqmrgpux_bsrsv_multiply", "tfqmrgpux_bsrsv_getVector",
-    "tfqmrgpux_bsrsv_getWindow", "tfqmrgpux_bsrsv_getRhsStatus", "tfqmrgpux_bsrsv_getSolveStats",
+    "tfqmrgpux_bsrsv_getWindow", "tfqmrgpux_bsrsv_getRhsStatus", "tfqmrgpux_bsrsv_getSolveStats", "tfqmrgpux_randomShadow",
 ]
 FORTRAN_SYMBOLS = [
     "tfqmrgpuprinterror_", "tfqmrgpucreatehandle_", "tfqmrgpudestroyhandle_", "tfqmrgpusetstream_",
@@ -113,6 +113,7 @@ def load():
     lib.tfqmrgpux_bsrsv_getWindow.argtypes = [vp, C.c_char, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     lib.tfqmrgpux_bsrsv_getRhsStatus.restype = st; lib.tfqmrgpux_bsrsv_getRhsStatus.argtypes = [vp, vp, vp]
     lib.tfqmrgpux_bsrsv_getSolveStats.restype = st; lib.tfqmrgpux_bsrsv_getSolveStats.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.tfqmrgpux_randomShadow.restype = st; lib.tfqmrgpux_randomShadow.argtypes = [vp, vp, C.c_size_t]
     _lib = lib
     return lib
 

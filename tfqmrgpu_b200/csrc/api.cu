@@ -433,6 +433,20 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getV3(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPla
     return TFQMRGPU_STATUS_SUCCESS;
 }
 
+tfqmrgpuStatus_t tfqmrgpux_randomShadow(tfqmrgpuHandle_t handle, float *devOut, size_t n) {
+    if (nullptr == handle || nullptr == devOut) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    cudaStream_t const stream = static_cast<Handle*>(handle)->stream;
+    curandGenerator_t gen;
+    if (CURAND_STATUS_SUCCESS != curandCreateGenerator(&gen, CURAND_RNG_PSEUDO_DEFAULT)) return TFQ_ERR(TFQMRGPU_STATUS_RANDOM_GEN_FAILED);
+    tfqmrgpuStatus_t st = TFQMRGPU_STATUS_SUCCESS;
+    if (CURAND_STATUS_SUCCESS != curandSetStream(gen, stream)) st = TFQ_ERR(TFQMRGPU_STATUS_RANDOM_GEN_FAILED);
+    else if (CURAND_STATUS_SUCCESS != curandSetPseudoRandomGeneratorSeed(gen, 1234ull)) st = TFQ_ERR(TFQMRGPU_STATUS_RANDOM_GEN_FAILED);
+    else if (CURAND_STATUS_SUCCESS != curandGenerateUniform(gen, devOut, n)) st = TFQ_ERR(TFQMRGPU_STATUS_RANDOM_GEN_FAILED);
+    cudaStreamSynchronize(stream);
+    curandDestroyGenerator(gen);
+    return st;
+}
+
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_multiply(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, int nrep) {
     if (nullptr == plan || nullptr == handle) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     Plan &p = *P(plan);
