@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Benchmark of the tfQMR hot path on B200 (driver contract: see the task statement).
+
+Workload (BASELINE.json configs[2], the largest single-GPU configuration the metric is quoted on):
+    synthetic 3-D 27-point block-stencil BSR operator, 32x32 complex fp32 blocks, 32^3 = 32768 block rows,
+    64 right-hand-side columns (2 block columns of 32), unit right-hand sides, sigma = 8, tolerance 1e-4.
+A "step" is one complete tfQMR solve of that system through the C-ABI of libtfQMRgpu.so.
+
+  value : whole-job solve throughput in GFLOP/s, flops counted with the reference's own convention
+          (tfqmrgpu_bsrsv_getInfo.flops_performed), A and B already resident in HBM;
+  e2e   : same metric through setMatrix(A) + setMatrix(B) + solve + getMatrix(X) with pinned HOST buffers,
+          host<->device copies inside the timed region;
+  roofline : the block-sparse product kernel (the dominant kernel), algorithmic bytes per launch over the
+          average launch duration measured with CUDA events on the solver's stream inside the timed steps;
+  cpu_baseline : the unmodified reference CPU build (oracle/_ref) - or the oracle port when that is not
+          available - on a bounded sample (6^3 block rows, same blocks / RHS / tolerance), N=1 rank 0 only.
+
+N > 1 (torchrun): every rank solves its own 64 right-hand-side columns of a 64*N-column problem with A
+replicated (RHS block-column sharding, no data-path collective); value = all ranks' flops / max time.
+`--impl reference` times the reference's CPU path on the bounded sample instead (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "tfqmr_solve_throughput"
+UNIT = "GFLOP/s"
+SAMPLE_N = 6
+
+
+def workload_name(n, lm, ln, ncols, prec):
+    return (f"stencil27 n={n}^3={n**3} block rows, {lm}x{ln} complex {'fp64' if prec == 'z' else 'fp32'} blocks, "
+            f"{ncols*ln} RHS columns per GPU, sigma=8, tol=1e-4")
+
+
+class Quiet:
+    """Silence C-level stdout chatter of the reference library while it runs."""
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.saved); os.close(self.null)
+
+
+def cpu_reference_sample(lm, ln, ncols, prec, tol, maxit, repeats=1):
+    """The reference's own CPU implementation (oracle/_ref/libtfqmr_ref_cpu.so, HAS_NO_CUDA build of the
+    unmodified sources) on the bounded sample; falls back to the oracle port when that .so is absent."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orclib as O
+    from tfqmrgpu_b200 import problems as P
+    dt = np.float64 if prec == "z" else np.float32
+    d = P.stencil27(SAMPLE_N, lm, ln, ncols, sigma=8.0, dtype=dt)
+    ref = O.ref_cpu()
+    times, flops, its = [], 0.0, 0
+    kind = "reference" if ref is not None else "port"
+    for _ in range(repeats):
+        if ref is not None:
+            with Quiet():
+                r = ref.solve(d["mb"], lm, ln, d["rpA"], d["ciA"], d["valA"].reshape(-1), d["rpX"], d["ciX"],
+                              d["rpB"], d["ciB"], d["valB"].reshape(-1), tol, maxit, prec)
+            times.append(r["t_solve"]); flops = r["flops"]; its = r["iterations"]
+        else:
+            op = O.OraclePlan(d["mb"], d["rpA"], d["ciA"], d["rpX"], d["ciX"], d["rpB"], d["ciB"])
+            A_int = O.import_blocks(d["valA"].reshape(-1), d["nnzbA"], lm, lm, var="A")
+            B_int = O.import_blocks(d["valB"].reshape(-1), d["nnzbB"], lm, ln, var="B")
+            v3 = O.v3_glibc(op.nnzbX*2*lm*ln)
+            t0 = time.perf_counter()
+            o = O.solve(op, lm, ln, A_int, B_int, v3, tol, maxit)
+            times.append(time.perf_counter() - t0); flops = o["flops"]; its = o["iterations"]
+    return dict(kind=kind, times=times, flops=flops, iterations=its,
+                sample=f"stencil27 n={SAMPLE_N}^3={SAMPLE_N**3} block rows (full size: 32^3), same {lm}x{ln} blocks, "
+                       f"{ncols*ln} RHS, tol {tol:g}: one complete solve ({its} iterations, {flops*1e-9:.1f} GFLOP)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    lm, ln, ncols, prec, tol, maxit = 32, 32, 2, "c", 1e-4, 100
+    cpu_reference_sample(lm, ln, ncols, prec, tol, maxit, repeats=args.warmup)
+    r = cpu_reference_sample(lm, ln, ncols, prec, tol, maxit, repeats=args.steps)
+    t = float(np.sum(r["times"]))
+    value = r["flops"]*args.steps/t*1e-9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3*t/args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.n, lm, ln, ncols, prec),
+                   "note": "reference CPU path (HAS_NO_CUDA build, serial solver) timed on a bounded sample of the workload"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": r["kind"], "sample": r["sample"],
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from tfqmrgpu_b200 import api, synthetic, _lib as L
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, lm, ln, ncols, prec, tol, maxit = args.n, args.lm, args.ln, args.ncols, args.precision, args.tol, 100
+    dt = np.float64 if prec == "z" else np.float32
+    es = 8 if prec == "z" else 4
+
+    # this rank's shard: block columns [rank*ncols, (rank+1)*ncols) of a world*ncols-column problem, A replicated
+    sp = synthetic.Stencil27(n, lm, ln, ncols, sigma=8.0, dtype=dt, device=dev, col0=rank*ncols, ncols_global=world*ncols)
+    h = api.Handle(torch.cuda.current_stream(dev).cuda_stream)
+    pl = api.BsrsvPlan(h, sp.mb, sp.rpA, sp.ciA, sp.rpX, sp.ciX, sp.rpB, sp.ciB)
+    nbytes = pl.buffer_size_for(lm, ln, prec)
+    pl.set_buffer()
+    info = pl.plan_info()
+    a_ptr = sp.valA_host.data_ptr()
+    valB = torch.from_numpy(sp.valB).pin_memory()
+    x_host = torch.empty(sp.nnzbX*lm*ln*2, dtype=torch.float64 if prec == "z" else torch.float32).pin_memory()
+    x_np = x_host.numpy()
+
+    def upload():
+        pl.set_matrix("A", None, "n", raw_ptr=a_ptr)
+        pl.set_matrix("B", None, "n", raw_ptr=valB.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+
+    def reduce_sum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.SUM); return float(t.item())
+
+    upload()
+    statuses = []
+    for _ in range(max(args.warmup, 3)):
+        statuses.append(pl.solve(tol, maxit))
+    # ---- device-resident metric: K solves, inputs already in HBM ------------------------------------------
+    pl.set_profiling(True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flops = launches = spmm_ms = spmm_n = iters = 0
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        statuses.append(pl.solve(tol, maxit))
+        prof = pl.solve_profile()
+        flops += pl.info()["flops"]; launches += prof["launches"]; spmm_ms += prof["spmm_ms"]; spmm_n += prof["spmm_launches"]
+        iters += prof["iterations"]
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = reduce_max(e0.elapsed_time(e1))
+    total_flops = reduce_sum(flops)
+    pl.set_profiling(False)
+    last = pl.info()
+
+    # ---- end to end through the C-ABI with host buffers -------------------------------------------------------
+    h2d = sp.a_bytes + valB.numel()*valB.element_size()
+    d2h = x_host.numel()*x_host.element_size()
+    e2e_flops = 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        upload()
+        pl.solve(tol, maxit)
+        pl.get_matrix("X", "n", L.LAYOUT_RIRIRIRI, out=x_np)
+        e2e_flops += pl.info()["flops"]
+    torch.cuda.synchronize(dev)
+    e2e_s = reduce_max(time.perf_counter() - t0)
+    e2e_total = reduce_sum(e2e_flops)
+
+    # ---- roofline of the block-sparse product ------------------------------------------------------------------
+    nPairs, nnzbX = info["nPairs"], info["nnzbX"]
+    lists_a_used = sp.nnzbA
+    spmm_bytes = lists_a_used*2*lm*lm*es + 2*nnzbX*2*lm*ln*es + 8*nPairs + 4*(nnzbX + 1)   # SURVEY.md 8d formula
+    spmm_flops = nPairs*8*lm*lm*ln
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "spmm_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    spmm_avg_ms = spmm_ms/max(spmm_n, 1)
+    achieved = spmm_bytes/(spmm_avg_ms*1e-3)*1e-9 if spmm_n else 0.0
+    roofline = {"bound": "hbm", "kernel": "spmm (block-sparse product Y=A*X)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved/peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
+                "launches_timed": int(spmm_n), "avg_launch_ms": spmm_avg_ms, "algorithmic_bytes_per_launch": spmm_bytes,
+                "gflops_per_launch": spmm_flops*1e-9, "achieved_tflops": spmm_flops/(spmm_avg_ms*1e-3)*1e-12 if spmm_n else 0.0,
+                "share_of_step": spmm_ms/max(e0.elapsed_time(e1), 1e-9)}
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": total_flops/(ms*1e-3)*1e-9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms/args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64" if prec == "z" else "f32", "data": "synthetic",
+            "config": {"workload": workload_name(n, lm, ln, ncols, prec), "parallelism": f"rhs-column sharding x{world}, A replicated",
+                       "l2": "working set 12 GB per GPU >> 126 MB L2, no flush needed",
+                       "iterations_per_solve": iters/args.steps, "residual_reached": last["residuum"], "status": int(statuses[-1]),
+                       "workspace_bytes": nbytes, "nnzbA": sp.nnzbA, "nnzbX": nnzbX, "nPairs": nPairs},
+            "e2e": {"value": e2e_total/e2e_s*1e-9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3*e2e_s/args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "clocks": clocks,
+        }
+    pl.close(); h.close()
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_reference_sample(lm, ln, ncols, prec, tol, maxit, repeats=1)
+        line["cpu_baseline"] = {"value": r["flops"]/r["times"][0]*1e-9, "unit": UNIT, "cores": 1, "kind": r["kind"],
+                                "sample": r["sample"], "host_cores_available": os.cpu_count()}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=32, help="grid edge (block rows = n^3); 32 is the BASELINE configuration")
+    ap.add_argument("--lm", type=int, default=32)
+    ap.add_argument("--ln", type=int, default=32)
+    ap.add_argument("--ncols", type=int, default=2, help="block columns of X per GPU")
+    ap.add_argument("--precision", default="c", choices=["c", "z"])
+    ap.add_argument("--tol", type=float, default=1e-4)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -66,6 +66,14 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getRhsStatus(tfqmrgpuHandle_t handle, tfqmrgpuB
  * host wall milliseconds inside solve, last max_bound^2, last target_bound^2, 0, 0 */
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_getSolveStats(tfqmrgpuBsrsvPlan_t plan, double stats[8]);
 
+/* Device-side profile of solves (off by default).  When on, solve records CUDA events on the handle's
+ * stream around the whole solve and around every A*v product of the iteration bodies.
+ * profile[0..7] of the last solve: device ms of the solve, summed device ms of the block-sparse products
+ * of the iterations that really ran, how many products that sum covers, iterations run, kernels launched,
+ * probes executed, 0, 0 */
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setProfiling(tfqmrgpuBsrsvPlan_t plan, int on);
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getSolveProfile(tfqmrgpuBsrsvPlan_t plan, double profile[8]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
 
 import numpy as np
 
@@ -262,7 +263,9 @@ class RefLib:
         assert lib.tfqmrgpu_bsrsv_setMatrix(h, plan, b"A", vA.ctypes.data, precision.encode(), lm, lm, tA.encode(), 0x55) == 0
         assert lib.tfqmrgpu_bsrsv_setMatrix(h, plan, b"B", vB.ctypes.data, precision.encode(), ln, lm, trans_b.encode(), 0x55) == 0
         lists = self._lists(plan)
+        t0 = time.perf_counter()
         status = lib.tfqmrgpu_bsrsv_solve(h, plan, float(tol), int(maxit))
+        t_solve = time.perf_counter() - t0
         res = C.c_double(); it = C.c_int32(); fl = C.c_double(); fla = C.c_double()
         lib.tfqmrgpu_bsrsv_getInfo(h, plan, C.byref(res), C.byref(it), C.byref(fl), C.byref(fla))
         Xint = np.zeros((nX, 2, lm, ln), dt)
@@ -274,7 +277,7 @@ class RefLib:
             lib.tfqmrgpuDestroyWorkspace(buf)
         lib.tfqmrgpuDestroyHandle(h)
         return dict(status=status, X=Xint, iterations=it.value, residuum=res.value, flops=fl.value,
-                    buffer_size=size.value, v3=v3_used, lists=lists)
+                    buffer_size=size.value, v3=v3_used, lists=lists, t_solve=t_solve)
 
 
 _ref_cpu = None

@@ -13,12 +13,11 @@
 #include <cstring>
 #include <vector>
 
+#ifndef HAS_NO_CUDA
+  #include <cuda_runtime.h>   // before the reference headers: tfqmrgpu.hxx #defines devPtr
+#endif
 #include "tfqmrgpu.hxx"       // reference: cuda.h or cudaStubs, tfqmrgpu.h, colIndex_t
 #include "tfqmrgpu_plan.hxx"  // reference: bsrsv_plan_t (tfqmrgpu_plan.hxx:9-55)
-
-#ifndef HAS_NO_CUDA
-  #include <cuda_runtime.h>
-#endif
 
 namespace {
     inline bsrsv_plan_t* P(void* plan) { return reinterpret_cast<bsrsv_plan_t*>(plan); }

@@ -4,7 +4,7 @@
  * Plain-C restatement of the tfQMRgpu hot path (plan analysis, BSR block-sparse multiply,
  * per-column tfQMR vector algebra, decisions and the host-side convergence logic).
  * Every function cites the reference file:line it follows (paths relative to /root/reference).
- * Pinned against the unmodified reference built in oracle/_ref (tests/test_oracle_pin.py) and
+ * Pinned against the unmodified reference built in oracle/_ref (tests/test_oracle_golden.py) and
  * against the committed golden vectors in tests/golden/.
  */
 #ifndef TFQMR_ORACLE_H

@@ -7,6 +7,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))  # orclib: bindings of the test-only oracle
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 

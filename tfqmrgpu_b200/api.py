@@ -204,6 +204,14 @@ class BsrsvPlan:
         _check(self.lib.tfqmrgpux_bsrsv_getSolveStats(self.plan, s), "getSolveStats")
         return dict(probes=int(s[0]), launches=int(s[1]), bodies=int(s[2]), host_ms=s[3], max_bound2=s[4], target_bound2=s[5])
 
+    def set_profiling(self, on=True):
+        _check(self.lib.tfqmrgpux_bsrsv_setProfiling(self.plan, int(on)), "setProfiling")
+
+    def solve_profile(self) -> dict:
+        s = (C.c_double*8)()
+        _check(self.lib.tfqmrgpux_bsrsv_getSolveProfile(self.plan, s), "getSolveProfile")
+        return dict(solve_ms=s[0], spmm_ms=s[1], spmm_launches=int(s[2]), iterations=int(s[3]), launches=int(s[4]), probes=int(s[5]))
+
     def close(self):
         if self.plan:
             self.lib.tfqmrgpu_bsrsv_destroyPlan(self.handle.h, self.plan)

@@ -298,6 +298,19 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_getInfo(tfqmrgpuHandle_t, tfqmrgpuBsrsvPlan_t pl
     return any ? TFQMRGPU_STATUS_SUCCESS : TFQMRGPU_STATUS_NO_INFO_PASSED;
 }
 
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setProfiling(tfqmrgpuBsrsvPlan_t plan, int on) {
+    if (nullptr == plan) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    P(plan)->profile = (0 != on);
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getSolveProfile(tfqmrgpuBsrsvPlan_t plan, double profile[8]) {
+    if (nullptr == plan || nullptr == profile) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan const &p = *P(plan);
+    profile[0] = p.prof_solve_ms; profile[1] = p.prof_spmm_ms; profile[2] = p.prof_spmm_launches; profile[3] = p.prof_iterations;
+    profile[4] = p.stat_launches; profile[5] = p.stat_probes; profile[6] = 0; profile[7] = 0;
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
 } // extern "C"
 
 // ---- quick starters: tfqmrgpu.cu:702-821 ------------------------------------------------------------

@@ -319,6 +319,7 @@ void plan_release(Plan &p) {
     cudaFree(p.d_perm); cudaFree(p.d_iperm); cudaFree(p.d_bpos);
     if (p.h_ctl) cudaFreeHost(p.h_ctl);
     for (auto &e : p.ev) if (e) cudaEventDestroy(e);
+    for (auto &e : p.prof_ev) if (e) cudaEventDestroy(e);
 }
 
 tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, char precision)

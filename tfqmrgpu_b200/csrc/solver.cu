@@ -35,6 +35,14 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
     }
     Control *const d_ctl = ws<Control>(p, p.off_ctl);
     double launches = 0;
+    // profiling: CUDA events on the solver's own stream around the solve and around every A*v6 product
+    constexpr int kProfBodies = 256;
+    if (p.profile && p.prof_ev.empty()) {
+        p.prof_ev.resize(2 + 4*kProfBodies, nullptr);
+        for (auto &e : p.prof_ev) TFQ_CUDA(cudaEventCreate(&e));
+    }
+    auto mark = [&](int which) { return p.profile ? cudaEventRecord(p.prof_ev[which], stream) : cudaSuccess; };
+    TFQ_CUDA(mark(0));
 
     // ---- initial state (core.hxx:114-131,170-174) ----------------------------------------------------
     Control &c0 = p.h_ctl[7];
@@ -76,12 +84,17 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
             if (STATE_DONE == p.h_ctl[slot].state) break;
         }
         // ---- one tfQMR iteration (core.hxx:189-233); all kernels are no-ops unless state == RUN ------
+        bool const prof = p.profile && (i < kProfBodies);
         TFQ_DO(launch_vecop(p, OP_K1, stream));
+        if (prof) TFQ_CUDA(mark(2 + 4*i));
         TFQ_DO(launch_spmm(p, v9, v6, STATE_RUN, stream));                 // v9 := A*v6     (core.hxx:198)
+        if (prof) TFQ_CUDA(mark(3 + 4*i));
         TFQ_DO(launch_vecop(p, OP_E1, stream));
         TFQ_DO(launch_vecop(p, OP_K2, stream));
         TFQ_DO(launch_vecop(p, OP_K3, stream));
+        if (prof) TFQ_CUDA(mark(4 + 4*i));
         TFQ_DO(launch_spmm(p, v8, v6, STATE_RUN, stream));                 // v8 := A*v6     (core.hxx:224)
+        if (prof) TFQ_CUDA(mark(5 + 4*i));
         TFQ_DO(launch_vecop(p, OP_E2, stream));
         TFQ_DO(launch_vecop(p, OP_K4, stream));
         // ---- residual probe (core.hxx:263-304); no-ops unless the device asked for it ---------------
@@ -96,8 +109,21 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
 #undef TFQ_DO
     Control &fin = p.h_ctl[6];
     TFQ_CUDA(cudaMemcpyAsync(&fin, d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, stream));
+    TFQ_CUDA(mark(1));
     TFQ_CUDA(cudaStreamSynchronize(stream));
     TFQ_CUDA(cudaGetLastError());
+    if (p.profile) {
+        float ms = 0;
+        TFQ_CUDA(cudaEventElapsedTime(&ms, p.prof_ev[0], p.prof_ev[1]));
+        p.prof_solve_ms = ms; p.prof_spmm_ms = 0; p.prof_spmm_launches = 0; p.prof_iterations = fin.iteration;
+        // only the bodies that really iterated: later ones were no-ops (state != RUN)
+        for (int i = 0; i < fin.iteration && i < kProfBodies && i < bodies; ++i) {
+            for (int h = 0; h < 2; ++h) {
+                TFQ_CUDA(cudaEventElapsedTime(&ms, p.prof_ev[2 + 4*i + 2*h], p.prof_ev[3 + 4*i + 2*h]));
+                p.prof_spmm_ms += ms; p.prof_spmm_launches += 1;
+            }
+        }
+    }
 
     // ---- bookkeeping (core.hxx:133-138,324-325; flop formula of SURVEY.md a14) ------------------------
     double const N = double(p.nnzbX)*p.LM*p.LN;

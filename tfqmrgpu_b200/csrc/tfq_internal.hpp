@@ -100,6 +100,10 @@ struct Plan {
     double residuum_reached = 0, flops_performed = -1, flops_performed_all = 0;
     int    iterations_needed = -1;
     double stat_probes = 0, stat_launches = 0, stat_bodies = 0, stat_ms = 0, stat_bound2 = 0, stat_target2 = 0;
+    // optional device-side profile of the last solve (tfqmrgpux_bsrsv_setProfiling)
+    bool   profile = false;
+    std::vector<cudaEvent_t> prof_ev;  // [0],[1] bracket the solve; 4 per iteration body bracket its two A*v6 products
+    double prof_solve_ms = 0, prof_spmm_ms = 0, prof_spmm_launches = 0, prof_iterations = 0;
 };
 
 // ---- plan analysis (plan.cu) ---------------------------------------------------------------------

@@ -159,7 +159,7 @@ def random_system(mb: int, lm: int, ln: int, ncols: int | None = None, pA: float
 # ------------------------------------------------------------------------------------------------
 def _hash_uniform(idx: np.ndarray, seed: int) -> np.ndarray:
     """Counter-based hash -> uniform(-1,1) doubles; identical on every host (no RNG state)."""
-    x = (idx.astype(np.uint64) + np.uint64(seed)*np.uint64(0x9E3779B97F4A7C15)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    x = idx.astype(np.uint64) + np.uint64((int(seed)*0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
     x ^= x >> np.uint64(30); x = (x*np.uint64(0xBF58476D1CE4E5B9)) & np.uint64(0xFFFFFFFFFFFFFFFF)
     x ^= x >> np.uint64(27); x = (x*np.uint64(0x94D049BB133111EB)) & np.uint64(0xFFFFFFFFFFFFFFFF)
     x ^= x >> np.uint64(31)
@@ -185,23 +185,29 @@ def stencil27_pattern(n: int) -> tuple[np.ndarray, np.ndarray]:
     return rp, cols.reshape(-1).astype(np.int32)
 
 
+def stencil27_values_rows(rp: np.ndarray, ci: np.ndarray, lm: int, sigma: float, blocks: np.ndarray,
+                          seed: int = 1234, dtype=np.float32) -> np.ndarray:
+    """Host-layout values real[len(blocks), lm, lm, 2] of the A blocks with indices ``blocks``: diagonal block
+    (27+sigma)*I + 0.05*U, off-diagonal -I + 0.05*U, U complex uniform(-1,1) from a hash of
+    (block, i, k, re/im, seed).  Pure function of the block index, so any subset can be regenerated."""
+    blocks = np.asarray(blocks, dtype=np.int64)
+    rows = np.searchsorted(rp, blocks, side="right") - 1
+    per = lm*lm*2
+    idx = (blocks.astype(np.uint64)[:, None]*np.uint64(per) + np.arange(per, dtype=np.uint64)[None, :])
+    u = _hash_uniform(idx, seed).reshape(blocks.size, lm, lm, 2)*0.05
+    diag = (rows == ci[blocks])
+    u[..., 0] += np.where(diag, 27. + sigma, -1.)[:, None, None]*np.eye(lm)[None]
+    return u.astype(dtype)
+
+
 def stencil27_values(rp: np.ndarray, ci: np.ndarray, lm: int, sigma: float, seed: int = 1234,
                      dtype=np.float32, chunk: int = 1 << 14) -> np.ndarray:
-    """Host-layout values real[nnzb, lm, lm, 2]: diagonal block (27+sigma)*I + 0.05*U, off-diagonal
-    -I + 0.05*U, U complex uniform(-1,1) from a hash of (block, i, k, re/im, seed)."""
+    """All A blocks, real[nnzb, lm, lm, 2] (see stencil27_values_rows)."""
     nnzb = int(ci.shape[0])
-    rows = np.repeat(np.arange(rp.shape[0] - 1), np.diff(rp))
     out = np.empty((nnzb, lm, lm, 2), dtype=dtype)
-    eye = np.eye(lm)
-    per = lm*lm*2
     for b0 in range(0, nnzb, chunk):
         b1 = min(nnzb, b0 + chunk)
-        idx = (np.arange(b0, b1, dtype=np.uint64)[:, None]*np.uint64(per)
-               + np.arange(per, dtype=np.uint64)[None, :])
-        u = _hash_uniform(idx, seed).reshape(b1 - b0, lm, lm, 2)*0.05
-        diag = (rows[b0:b1] == ci[b0:b1])
-        u[..., 0] += np.where(diag, 27. + sigma, -1.)[:, None, None]*eye[None]
-        out[b0:b1] = u.astype(dtype)
+        out[b0:b1] = stencil27_values_rows(rp, ci, lm, sigma, np.arange(b0, b1), seed, dtype)
     return out
 
 
