@@ -414,7 +414,7 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getPlanInfo(tfqmrgpuBsrsvPlan_t plan, int64_t i
     if (nullptr == plan || nullptr == info) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     Plan const &p = *P(plan);
     int64_t const v[16] = {p.nnzbX, p.nnzbB, p.nnzbA, int64_t(p.nCols), int64_t(p.nPairs), p.LM, p.LN, p.precision,
-                           int64_t(p.nTiles), int64_t(p.nUnits), int64_t(p.gmax), int64_t(p.nEntries), p.mb, 0, 0, 0};
+                           int64_t(p.nTiles), int64_t(p.nUnits), int64_t(p.gmax), int64_t(p.nEntries), p.mb, int64_t(p.use_tc), 0, 0};
     std::memcpy(info, v, sizeof(v));
     return TFQMRGPU_STATUS_SUCCESS;
 }
@@ -504,7 +504,9 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getRhsStatus(tfqmrgpuHandle_t handle, tfqmrgpuB
     Plan const &p = *P(plan);
     if (nullptr == p.pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     cudaStream_t const stream = static_cast<Handle*>(handle)->stream;
-    TFQ_CUDA(cudaMemcpyAsync(statusHost, p.pBuffer + p.off_status, size_t(p.nCols)*p.LN, cudaMemcpyDeviceToHost, stream));
+    // snap = the status array as the reference's host sees it after the last completed iteration / probe
+    // (status itself already carries the dec35 verdict of the following iteration, which is fused into K4)
+    TFQ_CUDA(cudaMemcpyAsync(statusHost, p.pBuffer + p.off_snap, size_t(p.nCols)*p.LN, cudaMemcpyDeviceToHost, stream));
     TFQ_CUDA(cudaStreamSynchronize(stream));
     return TFQMRGPU_STATUS_SUCCESS;
 }

@@ -372,6 +372,9 @@ tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, ch
         g = std::min(g, p.maxColsPerRow);
         // keep one pipeline stage (A block + g X blocks, possibly k-chunked) reasonable: <= 48 KiB at 4 k-rows
         while (g > 1 && 2*4*(size_t(LM) + size_t(g)*LN)*s > 48*1024) --g;
+        char const *env = std::getenv("TFQMRGPU_TENSOR");
+        p.use_tc = spmm_tc_supported(LM, LN, precision) && !(env && '0' == env[0]);
+        if (p.use_tc) g = spmm_tc_columns_per_unit(LN);   // 128 MMA rows = g * 2 * LN
         p.gmax = uint32_t(g);
         std::vector<uint32_t> first, ng;
         for (int r = 0; r < p.mb; ++r) {

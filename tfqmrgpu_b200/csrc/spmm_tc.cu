@@ -1,0 +1,314 @@
+// Block-sparse product  Y = A * X  for complex fp32 on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+// Same role as spmm.cu (the reference's blocksparse_action_t::multiply + gemmNxNf,
+// tfqmrgpu_blocksparse.hxx:71-199, tfqmrgpu_blockmult.hxx:10-93), used where the SIMT kernel is bound by
+// the FP32 pipe (LM = 32: 55 flop per HBM byte).  The complex block product is
+// mapped to ONE real GEMM per (block row, A block):
+//
+//     D[m][n] += sum_k  Xop[m][k] * Aop[n][k]        m = (g, Re|Im of X, j)   -> 128 rows  (G*2*LN)
+//                                                    n = (Re|Im of A, i)      -> 2*LM columns
+//     Xop[(g,cx,j)][k] = X_g[cx][k][j]               Aop[(ca,i)][k] = A[ca][k][i]
+//
+// so D holds the four real products Xr*Ar, Xr*Ai, Xi*Ar, Xi*Ai and no tensor flop is wasted; the epilogue
+// combines them: Yr = XrAr - XiAi, Yi = XrAi + XiAr.   fp32 accuracy comes from the 3xTF32 split
+// x = hi + lo (both rounded to TF32, exact operands):  D += Xhi*Ahi + Xlo*Ahi + Xhi*Alo  (the dropped
+// lo*lo term is 2^-24 relative).
+//
+// Data movement per CTA (one "unit": a block row times G block columns):
+//   * X operand: global -> registers (coalesced over j) -> split -> tcgen05.st into TENSOR MEMORY; the MMA
+//     reads its 128 x K operand from TMEM, so X never touches shared memory;
+//   * A operand: global -> registers -> split -> shared memory in the canonical K-major no-swizzle
+//     layout of the tcgen05 shared-memory descriptor (8 x 16-byte core matrices), written linearly;
+//   * accumulator D: 128 lanes x 2*LM columns of TMEM; read back once per unit with tcgen05.ld.
+// Two operand stages (TMEM columns + shared memory) are recycled through mbarriers signalled by
+// tcgen05.commit; a single thread issues the MMAs; the loads of entry e+1 are in flight while entry e is
+// split and multiplied, and two CTAs per SM overlap each other's prologue/epilogue.
+#include "tfq_internal.hpp"
+
+namespace tfq {
+
+namespace {
+
+constexpr int kTcThreads = 256;
+constexpr uint32_t kTmemCols = 256;     // [0,128): accumulator, [128,256): two X operand stages of 64 columns
+constexpr uint32_t kTmemStage0 = 128;
+
+struct TcArgs {
+    float *y; float const *x; float const *A;
+    uint32_t const *unit_e0, *unit_y, *ent_a, *ent_x;
+    Control const *ctl; int expect; int gstride;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(void const *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return 0 != ok;
+}
+// bounded: a tensor-core pipeline that never signals is a bug and must fail loudly (launch error), not hang
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) if (spins > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor], TF32 inputs, fp32 accumulation; issued by ONE thread
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrive once all MMAs issued so far by this thread have completed
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, uint32_t const (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// x ~ hi + lo, both exactly representable in TF32 (10 explicit mantissa bits) and both rounded to NEAREST, so the
+// tensor core sees exact operands whatever its own conversion does:  |x - hi| <= 2^-12 |x|,  |x - hi - lo| <= 2^-23 |x|.
+// (A plain truncation split leaves a one-sided 2^-20 error that accumulates linearly over the k sum and lifted the
+// attainable tfQMR residual of the 27-point stencil system above 1e-4 - measured on B200.)
+__device__ __forceinline__ uint32_t round_tf32(float v) { return (__float_as_uint(v) + 0x1000u) & 0xffffe000u; }
+__device__ __forceinline__ void split_tf32(float v, uint32_t &hi, uint32_t &lo) {
+    hi = round_tf32(v);
+    lo = round_tf32(v - __uint_as_float(hi));
+}
+
+// shared-memory matrix descriptor, no swizzle.  K-major operand: core matrix = 8 rows (m or n) of 16 bytes (4 TF32 k
+// values); LBO = byte stride between core matrices along K, SBO = byte stride between 8-row groups along M/N
+__device__ __forceinline__ uint64_t smem_desc_noswizzle(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= uint64_t((saddr >> 4) & 0x3fff);
+    d |= uint64_t((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= uint64_t((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= uint64_t(1) << 46;                          // descriptor version of sm_100
+    return d;                                        // base offset 0, layout type 0 = no swizzle
+}
+
+template <int LM, int LN>
+__global__ void __launch_bounds__(kTcThreads, 2)
+spmm_tc_kernel(TcArgs const a)
+{
+    static_assert(LM == 32, "k range per thread is LM/2 = 16 (tcgen05.st .x16)");
+    static_assert(LN == 32 || LN == 64, "128 MMA rows = G * 2 * LN");
+    constexpr int G  = 64/LN;             // block columns per unit
+    constexpr int N  = 2*LM;              // MMA N: (Re|Im of A, i)
+    constexpr int KS = LM/8;              // k-steps of 8 (TF32) per entry
+    constexpr int ABLK = 2*LM*LM;         // floats of one A block
+    constexpr int XBLK = 2*LM*LN;
+    // B operand (the A block) in shared memory: K-major, no swizzle.  Core matrix = 8 n-rows of 16 bytes (4 k values);
+    // one k-step of 8 = two core-matrix columns LBO apart; 8-row groups along n are SBO apart.
+    // (MN-major TF32 operands return zeros on sm_100a - measured, see DESIGN.md - so the block is re-laid K-major here.)
+    constexpr uint32_t KSB = N*32;        // bytes of one k-step: [2 k-quads][N rows][4 k]
+    constexpr uint32_t LBO = N*16;
+    constexpr uint32_t SBO = 128;
+    // instruction descriptor: D fp32, A/B TF32, both K-major, N, M = 128
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+
+    if (a.expect >= 0 && a.ctl->state != a.expect) return; // device-resident solver control
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    uint64_t *const bars = reinterpret_cast<uint64_t*>(smem_raw);           // [2]
+    uint32_t *const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 16);
+    uint32_t *const s_y = reinterpret_cast<uint32_t*>(smem_raw + 32);       // [G]
+    float *const stage_mem = reinterpret_cast<float*>(smem_raw + 1024);     // [2 stages][hi|lo][ABLK]
+
+    int const tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    int const q = w & 3, h = w >> 2;
+    int const m = 32*q + lane;
+    int const g = m/(2*LN), cx = (m/LN) & 1, j = m % LN;
+
+    uint32_t const u = blockIdx.x;
+    uint32_t const e0 = a.unit_e0[u];
+    int const nE = int(a.unit_e0[u + 1] - e0);
+    int const gs = a.gstride;
+
+    if (tid < G) s_y[tid] = (tid < gs) ? a.unit_y[size_t(u)*gs + tid] : kNoBlock;
+    if (0 == tid) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (0 == w) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t const tmem_base = *tmem_slot;
+    uint32_t const iy = s_y[g];
+    bool const has_g = (g < gs) && (kNoBlock != iy);
+
+    if (nE > 0) {
+        float xn[16]; float4 an[2];
+        // global loads of entry e into registers
+        auto load_entry = [&](int e) {
+            uint32_t const ia = a.ent_a[e0 + e];
+            uint32_t const ix = has_g ? a.ent_x[size_t(e0 + e)*gs + g] : kNoBlock;
+            if (kNoBlock != ix) {
+                float const *xp = a.x + size_t(ix)*XBLK + size_t(cx)*LM*LN + size_t(16*h)*LN + j;
+                #pragma unroll
+                for (int r = 0; r < 16; ++r) xn[r] = __ldg(xp + r*LN);
+            } else {
+                #pragma unroll
+                for (int r = 0; r < 16; ++r) xn[r] = 0.f;
+            }
+            float const *ap = a.A + size_t(ia)*ABLK;
+            #pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) {
+                int const c = tid + kTcThreads*c2;         // 4 consecutive k at one n; linear in shared memory
+                int const n = c % N, kq = c / N;
+                int const ca = n/LM, i = n % LM;
+                float const *src = ap + ca*LM*LM + (4*kq)*LM + i;   // a warp reads 32 consecutive i per k: coalesced
+                an[c2] = make_float4(__ldg(src), __ldg(src + LM), __ldg(src + 2*LM), __ldg(src + 3*LM));
+            }
+        };
+        load_entry(0);
+
+        for (int e = 0; e < nE; ++e) {
+            int const s = e & 1;
+            float xc[16]; float4 ac[2];
+            #pragma unroll
+            for (int r = 0; r < 16; ++r) xc[r] = xn[r];
+            ac[0] = an[0]; ac[1] = an[1];
+            if (e + 1 < nE) load_entry(e + 1);              // in flight during the split / MMA of entry e
+
+            if (e >= 2) { mbar_wait(&bars[s], unsigned(((e >> 1) - 1) & 1)); tc_fence_after(); } // stage s is free again
+
+            // ---- X operand: split, registers -> tensor memory (lane = m, column = k) --------------------
+            {
+                uint32_t hi[16], lo[16];
+                #pragma unroll
+                for (int r = 0; r < 16; ++r) split_tf32(xc[r], hi[r], lo[r]);
+                uint32_t const t0 = tmem_base + (uint32_t(32*q) << 16) + kTmemStage0 + uint32_t(s)*64 + uint32_t(16*h);
+                tmem_st16(t0, hi);
+                tmem_st16(t0 + 32, lo);
+            }
+            // ---- A operand: split, registers -> shared memory (canonical K-major layout, linear) ----------
+            {
+                float *const ahi = stage_mem + size_t(s)*2*ABLK, *const alo = ahi + ABLK;
+                #pragma unroll
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    int const c = tid + kTcThreads*c2;
+                    uint4 vh, vl;
+                    split_tf32(ac[c2].x, vh.x, vl.x); split_tf32(ac[c2].y, vh.y, vl.y);
+                    split_tf32(ac[c2].z, vh.z, vl.z); split_tf32(ac[c2].w, vh.w, vl.w);
+                    reinterpret_cast<uint4*>(ahi)[c] = vh;
+                    reinterpret_cast<uint4*>(alo)[c] = vl;
+                }
+            }
+            tmem_wait_st();
+            fence_proxy_async();       // generic-proxy shared-memory writes -> visible to the tensor core
+            tc_fence_before();
+            __syncthreads();
+            if (0 == tid) {
+                tc_fence_after();
+                uint32_t const sa_hi = smem_u32(stage_mem + size_t(s)*2*ABLK), sa_lo = sa_hi + ABLK*4;
+                uint32_t const xa = tmem_base + kTmemStage0 + uint32_t(s)*64;
+                #pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    uint64_t const bhi = smem_desc_noswizzle(sa_hi + ks*KSB, LBO, SBO);
+                    uint64_t const blo = smem_desc_noswizzle(sa_lo + ks*KSB, LBO, SBO);
+                    mma_tf32_ts(tmem_base, xa + 32 + 8*ks, bhi, IDESC, (e > 0 || ks > 0) ? 1u : 0u); // Xlo * Ahi
+                    mma_tf32_ts(tmem_base, xa + 8*ks,      blo, IDESC, 1u);                          // Xhi * Alo
+                    mma_tf32_ts(tmem_base, xa + 8*ks,      bhi, IDESC, 1u);                          // Xhi * Ahi
+                }
+                mma_commit(&bars[s]);
+            }
+        }
+        // all MMAs complete when the last commit has arrived (they retire in order)
+        mbar_wait(&bars[(nE - 1) & 1], unsigned(((nE - 1) >> 1) & 1));
+        tc_fence_after();
+    }
+
+    // ---- epilogue: D -> registers, combine the four real products, store Y ---------------------------------
+    float *const exch = stage_mem;      // [G][2][LM][LN] floats, aliases the operand stages (MMAs are done)
+    uint32_t d[32];
+    if (nE > 0) {
+        tmem_ld32(tmem_base + (uint32_t(32*q) << 16) + uint32_t(h)*LM, d);   // D[m][(ca = h, i = 0..31)]
+        tmem_wait_ld();
+    } else {
+        #pragma unroll
+        for (int i = 0; i < 32; ++i) d[i] = 0u;
+    }
+    if (1 == cx) {
+        #pragma unroll
+        for (int i = 0; i < LM; ++i) exch[((g*2 + h)*LM + i)*LN + j] = __uint_as_float(d[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (0 == cx && has_g) {
+        float *const yp = a.y + size_t(iy)*XBLK + size_t(h)*LM*LN + j;       // plane h: 0 = Re, 1 = Im
+        float const sgn = h ? 1.f : -1.f;                                     // Yr = XrAr - XiAi ; Yi = XrAi + XiAr
+        #pragma unroll
+        for (int i = 0; i < LM; ++i) yp[i*LN] = __uint_as_float(d[i]) + sgn*exch[((g*2 + (1 - h))*LM + i)*LN + j];
+    }
+    if (0 == w) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+template <int LM, int LN>
+tfqmrgpuStatus_t launch_tc(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream)
+{
+    constexpr size_t smem = 1024 + 2*2*size_t(2*LM*LM)*sizeof(float) + 1024; // barriers + two hi/lo stages (+ alignment slack)
+    // two CTAs per SM (two 256-column TMEM allocations): pad the request so that a third CTA can never be resident
+    constexpr size_t smem_req = (smem < 80*1024) ? 80*1024 : smem;
+    auto kernel = spmm_tc_kernel<LM, LN>;
+    static bool configured = false;
+    if (!configured) {
+        TFQ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_req)));
+        configured = true;
+    }
+    TcArgs a;
+    a.y = static_cast<float*>(y); a.x = static_cast<float const*>(x); a.A = ws<float const>(p, p.off_A);
+    a.unit_e0 = p.d_unit_e0; a.unit_y = p.d_unit_y; a.ent_a = p.d_ent_a; a.ent_x = p.d_ent_x;
+    a.ctl = ws<Control const>(p, p.off_ctl); a.expect = expect; a.gstride = int(p.gmax);
+    if (p.nUnits > 0) kernel<<<p.nUnits, kTcThreads, smem_req, stream>>>(a);
+    TFQ_CUDA(cudaGetLastError());
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+} // namespace
+
+bool spmm_tc_supported(int LM, int LN, char precision) {
+    return ('c' == precision) && (32 == LM) && (32 == LN || 64 == LN);
+}
+int spmm_tc_columns_per_unit(int LN) { return 64/LN; }
+
+tfqmrgpuStatus_t launch_spmm_tc(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream)
+{
+    if (32 == p.LM && 32 == p.LN) return launch_tc<32, 32>(p, y, x, expect, stream);
+    if (32 == p.LM && 64 == p.LN) return launch_tc<32, 64>(p, y, x, expect, stream);
+    return TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED);
+}
+
+} // namespace tfq

@@ -75,6 +75,7 @@ struct Plan {
     uint32_t *d_coltile = nullptr;    // [nCols+1] first tile of every block column
     // block-size dependent: SpMM units (one CTA each): a block row times <= gmax block columns
     uint32_t nUnits = 0, gmax = 1; uint64_t nEntries = 0;
+    bool use_tc = false;              // block-sparse product on the tensor cores (spmm_tc.cu)
     uint32_t *d_unit_e0 = nullptr;    // [nUnits+1] first entry of every unit
     uint32_t *d_unit_y = nullptr;     // [nUnits*gmax] storage index of the unit's Y blocks (kNoBlock = none)
     uint32_t *d_ent_a = nullptr;      // [nEntries] A block of the entry
@@ -116,6 +117,10 @@ void plan_release(Plan &p);
 // ---- kernels' host launchers --------------------------------------------------------------------
 // block-sparse product y = A*x on storage-ordered vectors; gate: run only if ctl->state == expect (expect < 0: always)
 tfqmrgpuStatus_t launch_spmm(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream);
+// tcgen05 3xTF32 variant (spmm_tc.cu): complex fp32, LM = 32; switch off with TFQMRGPU_TENSOR=0
+bool spmm_tc_supported(int LM, int LN, char precision);
+int  spmm_tc_columns_per_unit(int LN);
+tfqmrgpuStatus_t launch_spmm_tc(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream);
 // fused vector algebra, see vecops.cu
 enum VecOp : int { OP_INIT = 0, OP_K1, OP_E1, OP_K2, OP_K3, OP_E2, OP_K4, OP_N3, OP_COUNT };
 tfqmrgpuStatus_t launch_vecop(Plan const &p, int op, cudaStream_t stream);

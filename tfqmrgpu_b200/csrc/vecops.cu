@@ -388,7 +388,11 @@ vec_kernel(VecArgs<real_t> const a)
             double const res2 = red[j]*a.invBn2[s];
             double notdone = 0;
             if (res2 > tol2) { if (0 == a.snap[s]) notdone = 1; }
-            else if (res2 <= 0) { if (a.status[s] == a.snap[s]) a.status[s] = 1; }
+            else if (res2 <= 0) {           // core.hxx:282-285: the host marks the component as converged
+                // the fused dec35 of the NEXT iteration has already run; keep its verdict if it changed the status
+                if (a.status[s] == a.snap[s]) a.status[s] = 1;
+                a.snap[s] = 1;              // snap = the reference's status_h (what getRhsStatus reports)
+            }
             mon[j] = res2; mon[LN + j] = notdone;
         }
         __syncthreads();
