@@ -258,7 +258,7 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_setMatrix(tfqmrgpuHandle_t handle, tfqmrgpuBsrsv
     if ('a' == v) {
         char *const dst = p.pBuffer + p.off_A;
         TFQ_CUDA(cudaMemcpyAsync(dst, val, size_t(nnzb)*2*p.LM*p.LM*s, cudaMemcpyHostToDevice, stream));
-        return convert_inplace(p, dst, nnzb, p.LM, p.LM, is_double, layout, trans, scal_imag, stream);
+        return convert_inplace(p, dst, nnzb, p.LM, p.LM, is_double, layout, trans, scal_imag, stream, p.use_tc);
     }
     if ('b' == v) {
         char *const dst = p.pBuffer + p.off_B;

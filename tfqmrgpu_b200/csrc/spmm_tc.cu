@@ -17,12 +17,14 @@
 // Data movement per CTA (one "unit": a block row times G block columns):
 //   * X operand: global -> registers (coalesced over j) -> split -> tcgen05.st into TENSOR MEMORY; the MMA
 //     reads its 128 x K operand from TMEM, so X never touches shared memory;
-//   * A operand: global -> registers -> split -> shared memory in the canonical K-major no-swizzle
-//     layout of the tcgen05 shared-memory descriptor (8 x 16-byte core matrices), written linearly;
+//   * A operand: setMatrix('A') stores these blocks in HBM already in the canonical K-major no-swizzle layout
+//     of the tcgen05 shared-memory descriptor, so ONE bulk copy (cp.async.bulk, 8 KiB) per block into a
+//     6-deep ring delivers the hi operand as is (the tensor core truncates fp32 to TF32); the threads only
+//     derive lo = a - trunc(a) into a second buffer;
 //   * accumulator D: 128 lanes x 2*LM columns of TMEM; read back once per unit with tcgen05.ld.
-// Two operand stages (TMEM columns + shared memory) are recycled through mbarriers signalled by
-// tcgen05.commit; a single thread issues the MMAs; the loads of entry e+1 are in flight while entry e is
-// split and multiplied, and two CTAs per SM overlap each other's prologue/epilogue.
+// Two operand stages (TMEM columns + lo buffer) are recycled through mbarriers signalled by tcgen05.commit;
+// a single thread issues the MMAs and the bulk copies; the X loads of entry e+1 are in flight while entry e
+// is split and multiplied, and two CTAs per SM overlap each other's prologue/epilogue.
 #include "tfq_internal.hpp"
 
 namespace tfq {
@@ -30,7 +32,7 @@ namespace tfq {
 namespace {
 
 constexpr int kTcThreads = 256;
-constexpr uint32_t kTmemCols = 256;     // [0,128): accumulator, [128,256): two X operand stages of 64 columns
+constexpr uint32_t kTmemCols = 256;     // [0,64): accumulator, [64,128): correction accumulator, [128,256): two X operand stages
 constexpr uint32_t kTmemStage0 = 128;
 
 struct TcArgs {
@@ -43,6 +45,14 @@ __device__ __forceinline__ uint32_t smem_u32(void const *p) { return uint32_t(__
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (TMA engine without a tensor map), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, void const *src_gmem, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
     uint32_t ok;
@@ -97,15 +107,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// x ~ hi + lo, both exactly representable in TF32 (10 explicit mantissa bits) and both rounded to NEAREST, so the
-// tensor core sees exact operands whatever its own conversion does:  |x - hi| <= 2^-12 |x|,  |x - hi - lo| <= 2^-23 |x|.
-// (A plain truncation split leaves a one-sided 2^-20 error that accumulates linearly over the k sum and lifted the
-// attainable tfQMR residual of the 27-point stencil system above 1e-4 - measured on B200.)
-__device__ __forceinline__ uint32_t round_tf32(float v) { return (__float_as_uint(v) + 0x1000u) & 0xffffe000u; }
-__device__ __forceinline__ void split_tf32(float v, uint32_t &hi, uint32_t &lo) {
-    hi = round_tf32(v);
-    lo = round_tf32(v - __uint_as_float(hi));
+// 3xTF32 operand split  x ~ hi + lo.   The tensor core TRUNCATES an fp32 bit pattern to TF32 (measured on B200:
+// feeding the raw word or the word with its low 13 bits cleared gives bit-identical products), so
+//   * for the A blocks hi is the RAW word as the bulk copy delivered it, and lo = a - trunc(a) (exact in fp32);
+//   * for X, which passes through registers anyway, hi is rounded to NEAREST (|x - hi| <= 2^-12 |x|) and
+//     lo = x - hi (exact); the hardware's truncation of lo costs at most 2^-22 |x|.
+__device__ __forceinline__ void split_rn(float v, uint32_t &hi, uint32_t &lo) {
+    hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(v - __uint_as_float(hi));
 }
+__device__ __forceinline__ float lo_trunc(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
 // shared-memory matrix descriptor, no swizzle.  K-major operand: core matrix = 8 rows (m or n) of 16 bytes (4 TF32 k
 // values); LBO = byte stride between core matrices along K, SBO = byte stride between 8-row groups along M/N
@@ -118,6 +129,8 @@ __device__ __forceinline__ uint64_t smem_desc_noswizzle(uint32_t saddr, uint32_t
     return d;                                        // base offset 0, layout type 0 = no swizzle
 }
 
+constexpr int kRingA = 6;                            // raw A blocks in flight per CTA (bulk-copy ring)
+
 template <int LM, int LN>
 __global__ void __launch_bounds__(kTcThreads, 2)
 spmm_tc_kernel(TcArgs const a)
@@ -129,9 +142,9 @@ spmm_tc_kernel(TcArgs const a)
     constexpr int KS = LM/8;              // k-steps of 8 (TF32) per entry
     constexpr int ABLK = 2*LM*LM;         // floats of one A block
     constexpr int XBLK = 2*LM*LN;
-    // B operand (the A block) in shared memory: K-major, no swizzle.  Core matrix = 8 n-rows of 16 bytes (4 k values);
-    // one k-step of 8 = two core-matrix columns LBO apart; 8-row groups along n are SBO apart.
-    // (MN-major TF32 operands return zeros on sm_100a - measured, see DESIGN.md - so the block is re-laid K-major here.)
+    // B operand (the A block) in shared memory: K-major, no swizzle, [k/4][n][k%4] - the layout setMatrix('A') stores
+    // in HBM for these plans (layout.cu), so one bulk copy per block lands it ready for the MMA.
+    // (MN-major TF32 operands return zeros on sm_100a - measured, see DESIGN.md.)
     constexpr uint32_t KSB = N*32;        // bytes of one k-step: [2 k-quads][N rows][4 k]
     constexpr uint32_t LBO = N*16;
     constexpr uint32_t SBO = 128;
@@ -141,10 +154,12 @@ spmm_tc_kernel(TcArgs const a)
     if (a.expect >= 0 && a.ctl->state != a.expect) return; // device-resident solver control
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    uint64_t *const bars = reinterpret_cast<uint64_t*>(smem_raw);           // [2]
-    uint32_t *const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 16);
-    uint32_t *const s_y = reinterpret_cast<uint32_t*>(smem_raw + 32);       // [G]
-    float *const stage_mem = reinterpret_cast<float*>(smem_raw + 1024);     // [2 stages][hi|lo][ABLK]
+    uint64_t *const bar_mma = reinterpret_cast<uint64_t*>(smem_raw);        // [2]  MMAs of a stage have completed
+    uint64_t *const bar_a   = bar_mma + 2;                                  // [kRingA] raw A block has landed
+    uint32_t *const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 128);
+    uint32_t *const s_y = reinterpret_cast<uint32_t*>(smem_raw + 160);      // [G]
+    float *const ring   = reinterpret_cast<float*>(smem_raw + 1024);        // [kRingA][ABLK] raw A = hi operand
+    float *const lo_mem = ring + size_t(kRingA)*ABLK;                       // [2][ABLK]      lo operand
 
     int const tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     int const q = w & 3, h = w >> 2;
@@ -158,7 +173,9 @@ spmm_tc_kernel(TcArgs const a)
 
     if (tid < G) s_y[tid] = (tid < gs) ? a.unit_y[size_t(u)*gs + tid] : kNoBlock;
     if (0 == tid) {
-        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+        mbar_init(&bar_mma[0], 1); mbar_init(&bar_mma[1], 1);
+        #pragma unroll
+        for (int r = 0; r < kRingA; ++r) mbar_init(&bar_a[r], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (0 == w) tmem_alloc(tmem_slot, kTmemCols);
@@ -169,94 +186,106 @@ spmm_tc_kernel(TcArgs const a)
     uint32_t const iy = s_y[g];
     bool const has_g = (g < gs) && (kNoBlock != iy);
 
-    if (nE > 0) {
-        float xn[16]; float4 an[2];
-        // global loads of entry e into registers
-        auto load_entry = [&](int e) {
-            uint32_t const ia = a.ent_a[e0 + e];
-            uint32_t const ix = has_g ? a.ent_x[size_t(e0 + e)*gs + g] : kNoBlock;
-            if (kNoBlock != ix) {
-                float const *xp = a.x + size_t(ix)*XBLK + size_t(cx)*LM*LN + size_t(16*h)*LN + j;
-                #pragma unroll
-                for (int r = 0; r < 16; ++r) xn[r] = __ldg(xp + r*LN);
-            } else {
-                #pragma unroll
-                for (int r = 0; r < 16; ++r) xn[r] = 0.f;
-            }
-            float const *ap = a.A + size_t(ia)*ABLK;
+    // raw A block of entry e -> ring slot e % kRingA (one thread, bulk-copy engine)
+    auto fetch_a = [&](int e) {
+        int const r = e % kRingA;
+        uint32_t const ia = a.ent_a[e0 + e];
+        mbar_expect_tx(&bar_a[r], unsigned(ABLK*sizeof(float)));
+        bulk_g2s(ring + size_t(r)*ABLK, a.A + size_t(ia)*ABLK, unsigned(ABLK*sizeof(float)), &bar_a[r]);
+    };
+    if (0 == tid) for (int e = 0; e < kRingA && e < nE; ++e) fetch_a(e);
+
+    uint32_t const xoff = uint32_t(cx)*LM*LN + uint32_t(16*h)*LN + uint32_t(j);
+    auto x_index = [&](int e) -> uint32_t { return (has_g && e < nE) ? a.ent_x[size_t(e0 + e)*gs + g] : kNoBlock; };
+    auto load_x = [&](uint32_t ix, float (&xr)[16]) {
+        if (kNoBlock != ix) {
+            float const *xp = a.x + size_t(ix)*XBLK + xoff;
+            #pragma unroll
+            for (int r = 0; r < 16; ++r) xr[r] = __ldg(xp + r*LN);
+        } else {
+            #pragma unroll
+            for (int r = 0; r < 16; ++r) xr[r] = 0.f;
+        }
+    };
+
+    // one entry: xc holds its X values; the loads of entry e+1 go to xn while entry e is split and multiplied
+    auto step = [&](int e, float (&xc)[16], float (&xn)[16], uint32_t ix_next, uint32_t &ix_next2) {
+        int const s = e & 1, r = e % kRingA;
+        load_x(ix_next, xn);
+        ix_next2 = x_index(e + 2);
+        if (e >= 2) {                                        // stage s (TMEM columns, lo buffer) and ring slot (e-2) are free
+            mbar_wait(&bar_mma[s], unsigned(((e >> 1) - 1) & 1));
+            tc_fence_after();
+            if (0 == tid && e - 2 + kRingA < nE) fetch_a(e - 2 + kRingA);
+        }
+        // ---- X operand: split, registers -> tensor memory (lane = m, column = k) ------------------------
+        {
+            uint32_t hi[16], lo[16];
+            #pragma unroll
+            for (int t = 0; t < 16; ++t) split_rn(xc[t], hi[t], lo[t]);
+            uint32_t const t0 = tmem_base + (uint32_t(32*q) << 16) + kTmemStage0 + uint32_t(s)*64 + uint32_t(16*h);
+            tmem_st16(t0, hi);
+            tmem_st16(t0 + 32, lo);
+        }
+        // ---- A operand: hi = the raw block in the ring, lo = a - trunc(a) -> shared memory ------------------
+        mbar_wait(&bar_a[r], unsigned((e / kRingA) & 1));
+        {
+            float4 const *const src = reinterpret_cast<float4 const*>(ring + size_t(r)*ABLK);
+            float4 *const dst = reinterpret_cast<float4*>(lo_mem + size_t(s)*ABLK);
             #pragma unroll
             for (int c2 = 0; c2 < 2; ++c2) {
-                int const c = tid + kTcThreads*c2;         // 4 consecutive k at one n; linear in shared memory
-                int const n = c % N, kq = c / N;
-                int const ca = n/LM, i = n % LM;
-                float const *src = ap + ca*LM*LM + (4*kq)*LM + i;   // a warp reads 32 consecutive i per k: coalesced
-                an[c2] = make_float4(__ldg(src), __ldg(src + LM), __ldg(src + 2*LM), __ldg(src + 3*LM));
-            }
-        };
-        load_entry(0);
-
-        for (int e = 0; e < nE; ++e) {
-            int const s = e & 1;
-            float xc[16]; float4 ac[2];
-            #pragma unroll
-            for (int r = 0; r < 16; ++r) xc[r] = xn[r];
-            ac[0] = an[0]; ac[1] = an[1];
-            if (e + 1 < nE) load_entry(e + 1);              // in flight during the split / MMA of entry e
-
-            if (e >= 2) { mbar_wait(&bars[s], unsigned(((e >> 1) - 1) & 1)); tc_fence_after(); } // stage s is free again
-
-            // ---- X operand: split, registers -> tensor memory (lane = m, column = k) --------------------
-            {
-                uint32_t hi[16], lo[16];
-                #pragma unroll
-                for (int r = 0; r < 16; ++r) split_tf32(xc[r], hi[r], lo[r]);
-                uint32_t const t0 = tmem_base + (uint32_t(32*q) << 16) + kTmemStage0 + uint32_t(s)*64 + uint32_t(16*h);
-                tmem_st16(t0, hi);
-                tmem_st16(t0 + 32, lo);
-            }
-            // ---- A operand: split, registers -> shared memory (canonical K-major layout, linear) ----------
-            {
-                float *const ahi = stage_mem + size_t(s)*2*ABLK, *const alo = ahi + ABLK;
-                #pragma unroll
-                for (int c2 = 0; c2 < 2; ++c2) {
-                    int const c = tid + kTcThreads*c2;
-                    uint4 vh, vl;
-                    split_tf32(ac[c2].x, vh.x, vl.x); split_tf32(ac[c2].y, vh.y, vl.y);
-                    split_tf32(ac[c2].z, vh.z, vl.z); split_tf32(ac[c2].w, vh.w, vl.w);
-                    reinterpret_cast<uint4*>(ahi)[c] = vh;
-                    reinterpret_cast<uint4*>(alo)[c] = vl;
-                }
-            }
-            tmem_wait_st();
-            fence_proxy_async();       // generic-proxy shared-memory writes -> visible to the tensor core
-            tc_fence_before();
-            __syncthreads();
-            if (0 == tid) {
-                tc_fence_after();
-                uint32_t const sa_hi = smem_u32(stage_mem + size_t(s)*2*ABLK), sa_lo = sa_hi + ABLK*4;
-                uint32_t const xa = tmem_base + kTmemStage0 + uint32_t(s)*64;
-                #pragma unroll
-                for (int ks = 0; ks < KS; ++ks) {
-                    uint64_t const bhi = smem_desc_noswizzle(sa_hi + ks*KSB, LBO, SBO);
-                    uint64_t const blo = smem_desc_noswizzle(sa_lo + ks*KSB, LBO, SBO);
-                    mma_tf32_ts(tmem_base, xa + 32 + 8*ks, bhi, IDESC, (e > 0 || ks > 0) ? 1u : 0u); // Xlo * Ahi
-                    mma_tf32_ts(tmem_base, xa + 8*ks,      blo, IDESC, 1u);                          // Xhi * Alo
-                    mma_tf32_ts(tmem_base, xa + 8*ks,      bhi, IDESC, 1u);                          // Xhi * Ahi
-                }
-                mma_commit(&bars[s]);
+                float4 v = src[tid + kTcThreads*c2];
+                v.x = lo_trunc(v.x); v.y = lo_trunc(v.y); v.z = lo_trunc(v.z); v.w = lo_trunc(v.w);
+                dst[tid + kTcThreads*c2] = v;
             }
         }
+        tmem_wait_st();
+        fence_proxy_async();       // generic-proxy shared-memory writes -> visible to the tensor core
+        tc_fence_before();
+        __syncthreads();
+        if (0 == tid) {
+            tc_fence_after();
+            uint32_t const sa_hi = smem_u32(ring + size_t(r)*ABLK), sa_lo = smem_u32(lo_mem + size_t(s)*ABLK);
+            uint32_t const xa = tmem_base + kTmemStage0 + uint32_t(s)*64;
+            #pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                uint64_t const bhi = smem_desc_noswizzle(sa_hi + ks*KSB, LBO, SBO);
+                uint64_t const blo = smem_desc_noswizzle(sa_lo + ks*KSB, LBO, SBO);
+                uint32_t const first = (e > 0 || ks > 0) ? 1u : 0u;
+                // the two correction products go to their OWN accumulator: the tensor core truncates the fp32
+                // accumulator once per MMA, and 2/3 of those events would otherwise hit the large sum
+                mma_tf32_ts(tmem_base + N, xa + 32 + 8*ks, bhi, IDESC, first);   // Xlo * Ahi
+                mma_tf32_ts(tmem_base + N, xa + 8*ks,      blo, IDESC, 1u);      // Xhi * Alo
+                mma_tf32_ts(tmem_base,     xa + 8*ks,      bhi, IDESC, first);   // Xhi * Ahi
+            }
+            mma_commit(&bar_mma[s]);
+        }
+    };
+
+    if (nE > 0) {
+        float xa_[16], xb_[16];
+        uint32_t i1 = x_index(1), i2 = kNoBlock;
+        load_x(x_index(0), xa_);
+        for (int e = 0; e < nE; e += 2) {
+            step(e, xa_, xb_, i1, i2);                       // i2 := index of entry e+2
+            if (e + 1 < nE) step(e + 1, xb_, xa_, i2, i1);   // i1 := index of entry e+3
+            else break;
+        }
         // all MMAs complete when the last commit has arrived (they retire in order)
-        mbar_wait(&bars[(nE - 1) & 1], unsigned(((nE - 1) >> 1) & 1));
+        mbar_wait(&bar_mma[(nE - 1) & 1], unsigned(((nE - 1) >> 1) & 1));
         tc_fence_after();
     }
 
     // ---- epilogue: D -> registers, combine the four real products, store Y ---------------------------------
-    float *const exch = stage_mem;      // [G][2][LM][LN] floats, aliases the operand stages (MMAs are done)
+    float *const exch = ring;           // [G][2][LM][LN] floats, aliases the A ring (all MMAs are done)
     uint32_t d[32];
     if (nE > 0) {
-        tmem_ld32(tmem_base + (uint32_t(32*q) << 16) + uint32_t(h)*LM, d);   // D[m][(ca = h, i = 0..31)]
+        uint32_t d2[32];
+        tmem_ld32(tmem_base + (uint32_t(32*q) << 16) + uint32_t(h)*LM, d);       // D[m][(ca = h, i = 0..31)]
+        tmem_ld32(tmem_base + (uint32_t(32*q) << 16) + N + uint32_t(h)*LM, d2);  // correction terms
         tmem_wait_ld();
+        #pragma unroll
+        for (int i = 0; i < 32; ++i) d[i] = __float_as_uint(__uint_as_float(d[i]) + __uint_as_float(d2[i]));
     } else {
         #pragma unroll
         for (int i = 0; i < 32; ++i) d[i] = 0u;
@@ -279,7 +308,7 @@ spmm_tc_kernel(TcArgs const a)
 template <int LM, int LN>
 tfqmrgpuStatus_t launch_tc(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream)
 {
-    constexpr size_t smem = 1024 + 2*2*size_t(2*LM*LM)*sizeof(float) + 1024; // barriers + two hi/lo stages (+ alignment slack)
+    constexpr size_t smem = 1024 + (kRingA + 2)*size_t(2*LM*LM)*sizeof(float) + 1024; // barriers + A ring + two lo stages
     // two CTAs per SM (two 256-column TMEM allocations): pad the request so that a third CTA can never be resident
     constexpr size_t smem_req = (smem < 80*1024) ? 80*1024 : smem;
     auto kernel = spmm_tc_kernel<LM, LN>;

@@ -128,7 +128,7 @@ tfqmrgpuStatus_t launch_vecop(Plan const &p, int op, cudaStream_t stream);
 tfqmrgpuStatus_t launch_add_rhs(Plan const &p, void *v, double scal, int expect, cudaStream_t stream);
 // host layout <-> internal layout (layout.cu)
 tfqmrgpuStatus_t convert_inplace(Plan const &p, void *blocks, uint32_t nnzb, int rows, int cols, bool is_double,
-                                 int layout, bool trans, double scal_imag, cudaStream_t stream);
+                                 int layout, bool trans, double scal_imag, cudaStream_t stream, bool umma_kmajor = false);
 tfqmrgpuStatus_t convert_permuted(Plan const &p, void *dst, void const *src, uint32_t nnzb, int rows, int cols,
                                   bool is_double, int layout, bool trans, double scal_imag, bool to_internal,
                                   cudaStream_t stream);
