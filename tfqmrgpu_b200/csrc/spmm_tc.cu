@@ -23,15 +23,18 @@
 //     derive lo = a - trunc(a) into a second buffer;
 //   * accumulator D: 128 lanes x 2*LM columns of TMEM; read back once per unit with tcgen05.ld.
 // Two operand stages (TMEM columns + lo buffer) are recycled through mbarriers signalled by tcgen05.commit;
-// a single thread issues the MMAs and the bulk copies; the X loads of entry e+1 are in flight while entry e
-// is split and multiplied, and two CTAs per SM overlap each other's prologue/epilogue.
+// eight converter warps prepare the operands and never synchronise with each other inside the loop (they only
+// arrive on the stage's mbarrier), a ninth warp issues the bulk copies and the MMAs from one lane; the X loads
+// of entry e+1 are in flight while entry e is split, and two CTAs per SM overlap each other's
+// prologue/epilogue.
 #include "tfq_internal.hpp"
 
 namespace tfq {
 
 namespace {
 
-constexpr int kTcThreads = 256;
+constexpr int kConvWarps = 8, kConvThreads = 32*kConvWarps;   // converter warps; warp 8 issues copies and MMAs
+constexpr int kTcThreads = kConvThreads + 32;
 constexpr uint32_t kTmemCols = 256;     // [0,64): accumulator, [64,128): correction accumulator, [128,256): two X operand stages
 constexpr uint32_t kTmemStage0 = 128;
 
@@ -54,6 +57,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, void const *src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\t"
@@ -65,6 +71,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
 // bounded: a tensor-core pipeline that never signals is a bug and must fail loudly (launch error), not hang
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) if (spins > (1u << 24)) __trap();
+}
+__device__ __forceinline__ uint32_t elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %1;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred) : "r"(0xffffffffu));
+    return pred;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -154,18 +165,15 @@ spmm_tc_kernel(TcArgs const a)
     if (a.expect >= 0 && a.ctl->state != a.expect) return; // device-resident solver control
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    uint64_t *const bar_mma = reinterpret_cast<uint64_t*>(smem_raw);        // [2]  MMAs of a stage have completed
-    uint64_t *const bar_a   = bar_mma + 2;                                  // [kRingA] raw A block has landed
+    uint64_t *const bar_mma   = reinterpret_cast<uint64_t*>(smem_raw);      // [2]  MMAs of a stage have completed
+    uint64_t *const bar_ready = bar_mma + 2;                                // [2]  a stage's operands are in place
+    uint64_t *const bar_a     = bar_mma + 4;                                // [kRingA] raw A block has landed
     uint32_t *const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 128);
     uint32_t *const s_y = reinterpret_cast<uint32_t*>(smem_raw + 160);      // [G]
     float *const ring   = reinterpret_cast<float*>(smem_raw + 1024);        // [kRingA][ABLK] raw A = hi operand
     float *const lo_mem = ring + size_t(kRingA)*ABLK;                       // [2][ABLK]      lo operand
 
     int const tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    int const q = w & 3, h = w >> 2;
-    int const m = 32*q + lane;
-    int const g = m/(2*LN), cx = (m/LN) & 1, j = m % LN;
-
     uint32_t const u = blockIdx.x;
     uint32_t const e0 = a.unit_e0[u];
     int const nE = int(a.unit_e0[u + 1] - e0);
@@ -174,135 +182,152 @@ spmm_tc_kernel(TcArgs const a)
     if (tid < G) s_y[tid] = (tid < gs) ? a.unit_y[size_t(u)*gs + tid] : kNoBlock;
     if (0 == tid) {
         mbar_init(&bar_mma[0], 1); mbar_init(&bar_mma[1], 1);
+        mbar_init(&bar_ready[0], kConvWarps); mbar_init(&bar_ready[1], kConvWarps);
         #pragma unroll
         for (int r = 0; r < kRingA; ++r) mbar_init(&bar_a[r], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (0 == w) tmem_alloc(tmem_slot, kTmemCols);
+    if (kConvWarps == w) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t const tmem_base = *tmem_slot;
-    uint32_t const iy = s_y[g];
-    bool const has_g = (g < gs) && (kNoBlock != iy);
 
-    // raw A block of entry e -> ring slot e % kRingA (one thread, bulk-copy engine)
-    auto fetch_a = [&](int e) {
-        int const r = e % kRingA;
-        uint32_t const ia = a.ent_a[e0 + e];
-        mbar_expect_tx(&bar_a[r], unsigned(ABLK*sizeof(float)));
-        bulk_g2s(ring + size_t(r)*ABLK, a.A + size_t(ia)*ABLK, unsigned(ABLK*sizeof(float)), &bar_a[r]);
-    };
-    if (0 == tid) for (int e = 0; e < kRingA && e < nE; ++e) fetch_a(e);
+    if (kConvWarps == w) {
+        // ================= issuer warp: bulk copies of the A blocks and the MMAs =====================================
+        // The whole warp runs the loop converged and ONE elected lane issues: with elect.sync the compiler emits
+        // back-to-back UTCHMMA; a lane picked by "if (0 == lane)" costs an elect/branch loop (~125 cycles) per MMA.
+        uint32_t const leader = elect_one_sync();
+        auto fetch_a = [&](int e) {
+            int const r = e % kRingA;
+            uint32_t const ia = a.ent_a[e0 + e];
+            mbar_expect_tx(&bar_a[r], unsigned(ABLK*sizeof(float)));
+            bulk_g2s(ring + size_t(r)*ABLK, a.A + size_t(ia)*ABLK, unsigned(ABLK*sizeof(float)), &bar_a[r]);
+        };
+        if (leader) for (int e = 0; e < kRingA && e < nE; ++e) fetch_a(e);
+        uint32_t const ring_u32 = smem_u32(ring), lo_u32 = smem_u32(lo_mem);
+        for (int e = 0; e < nE; ++e) {
+            int const s = e & 1, r = e % kRingA;
+            if (e >= 2 && e - 2 + kRingA < nE) {                // ring slot of entry e-2 is free once its MMAs completed
+                mbar_wait(&bar_mma[s], unsigned(((e >> 1) - 1) & 1));
+                if (leader) fetch_a(e - 2 + kRingA);
+            }
+            mbar_wait(&bar_ready[s], unsigned((e >> 1) & 1));   // X in TMEM, lo in shared memory (and the raw A landed)
+            tc_fence_after();
+            if (leader) {
+                uint32_t const sa_hi = ring_u32 + uint32_t(r)*ABLK*4, sa_lo = lo_u32 + uint32_t(s)*ABLK*4;
+                uint32_t const xa = tmem_base + kTmemStage0 + uint32_t(s)*64;
+                #pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    uint64_t const bhi = smem_desc_noswizzle(sa_hi + ks*KSB, LBO, SBO);
+                    uint64_t const blo = smem_desc_noswizzle(sa_lo + ks*KSB, LBO, SBO);
+                    uint32_t const first = (e > 0 || ks > 0) ? 1u : 0u;
+                    // the two correction products go to their OWN accumulator: the tensor core truncates the fp32
+                    // accumulator once per MMA, and 2/3 of those events would otherwise hit the large sum
+                    mma_tf32_ts(tmem_base + N, xa + 32 + 8*ks, bhi, IDESC, first);   // Xlo * Ahi
+                    mma_tf32_ts(tmem_base + N, xa + 8*ks,      blo, IDESC, 1u);      // Xhi * Alo
+                    mma_tf32_ts(tmem_base,     xa + 8*ks,      bhi, IDESC, first);   // Xhi * Ahi
+                }
+                mma_commit(&bar_mma[s]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================= converter warps: X -> TMEM, lo(A) -> shared memory, epilogue ==============================
+        int const q = w & 3, h = w >> 2;
+        int const m = 32*q + lane;
+        int const g = m/(2*LN), cx = (m/LN) & 1, j = m % LN;
+        uint32_t const iy = s_y[g];
+        bool const has_g = (g < gs) && (kNoBlock != iy);
+        uint32_t const xoff = uint32_t(cx)*LM*LN + uint32_t(16*h)*LN + uint32_t(j);
+        auto x_index = [&](int e) -> uint32_t { return (has_g && e < nE) ? a.ent_x[size_t(e0 + e)*gs + g] : kNoBlock; };
+        auto load_x = [&](uint32_t ix, float (&xr)[16]) {
+            if (kNoBlock != ix) {
+                float const *xp = a.x + size_t(ix)*XBLK + xoff;
+                #pragma unroll
+                for (int r = 0; r < 16; ++r) xr[r] = __ldg(xp + r*LN);
+            } else {
+                #pragma unroll
+                for (int r = 0; r < 16; ++r) xr[r] = 0.f;
+            }
+        };
+        // one entry: xc holds its X values; the loads of entry e+1 go to xn while entry e is split
+        auto step = [&](int e, float (&xc)[16], float (&xn)[16], uint32_t ix_next, uint32_t &ix_next2) {
+            int const s = e & 1, r = e % kRingA;
+            load_x(ix_next, xn);
+            ix_next2 = x_index(e + 2);
+            if (e >= 2) { mbar_wait(&bar_mma[s], unsigned(((e >> 1) - 1) & 1)); tc_fence_after(); } // stage s is free again
+            // ---- X operand: split, registers -> tensor memory (lane = m, column = k) ------------------------
+            {
+                uint32_t hi[16], lo[16];
+                #pragma unroll
+                for (int t = 0; t < 16; ++t) split_rn(xc[t], hi[t], lo[t]);
+                uint32_t const t0 = tmem_base + (uint32_t(32*q) << 16) + kTmemStage0 + uint32_t(s)*64 + uint32_t(16*h);
+                tmem_st16(t0, hi);
+                tmem_st16(t0 + 32, lo);
+            }
+            // ---- A operand: hi = the raw block in the ring, lo = a - trunc(a) -> shared memory ------------------
+            mbar_wait(&bar_a[r], unsigned((e / kRingA) & 1));
+            {
+                float4 const *const src = reinterpret_cast<float4 const*>(ring + size_t(r)*ABLK);
+                float4 *const dst = reinterpret_cast<float4*>(lo_mem + size_t(s)*ABLK);
+                #pragma unroll
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    float4 v = src[tid + kConvThreads*c2];
+                    v.x = lo_trunc(v.x); v.y = lo_trunc(v.y); v.z = lo_trunc(v.z); v.w = lo_trunc(v.w);
+                    dst[tid + kConvThreads*c2] = v;
+                }
+            }
+            tmem_wait_st();
+            fence_proxy_async();       // generic-proxy shared-memory writes -> visible to the tensor core
+            tc_fence_before();
+            __syncwarp();
+            if (0 == lane) mbar_arrive(&bar_ready[s]);
+        };
 
-    uint32_t const xoff = uint32_t(cx)*LM*LN + uint32_t(16*h)*LN + uint32_t(j);
-    auto x_index = [&](int e) -> uint32_t { return (has_g && e < nE) ? a.ent_x[size_t(e0 + e)*gs + g] : kNoBlock; };
-    auto load_x = [&](uint32_t ix, float (&xr)[16]) {
-        if (kNoBlock != ix) {
-            float const *xp = a.x + size_t(ix)*XBLK + xoff;
+        if (nE > 0) {
+            float xa_[16], xb_[16];
+            uint32_t i1 = x_index(1), i2 = kNoBlock;
+            load_x(x_index(0), xa_);
+            for (int e = 0; e < nE; e += 2) {
+                step(e, xa_, xb_, i1, i2);                       // i2 := index of entry e+2
+                if (e + 1 < nE) step(e + 1, xb_, xa_, i2, i1);   // i1 := index of entry e+3
+                else break;
+            }
+            // all MMAs complete when the last commit has arrived (they retire in order)
+            mbar_wait(&bar_mma[(nE - 1) & 1], unsigned(((nE - 1) >> 1) & 1));
+            tc_fence_after();
+        }
+
+        // ---- epilogue: D -> registers, combine the four real products, store Y ---------------------------------
+        float *const exch = ring;           // [G][2][LM][LN] floats, aliases the A ring (all copies and MMAs are done)
+        uint32_t d[32];
+        if (nE > 0) {
+            uint32_t d2[32];
+            tmem_ld32(tmem_base + (uint32_t(32*q) << 16) + uint32_t(h)*LM, d);       // D[m][(ca = h, i = 0..31)]
+            tmem_ld32(tmem_base + (uint32_t(32*q) << 16) + N + uint32_t(h)*LM, d2);  // correction terms
+            tmem_wait_ld();
             #pragma unroll
-            for (int r = 0; r < 16; ++r) xr[r] = __ldg(xp + r*LN);
+            for (int i = 0; i < 32; ++i) d[i] = __float_as_uint(__uint_as_float(d[i]) + __uint_as_float(d2[i]));
         } else {
             #pragma unroll
-            for (int r = 0; r < 16; ++r) xr[r] = 0.f;
+            for (int i = 0; i < 32; ++i) d[i] = 0u;
         }
-    };
-
-    // one entry: xc holds its X values; the loads of entry e+1 go to xn while entry e is split and multiplied
-    auto step = [&](int e, float (&xc)[16], float (&xn)[16], uint32_t ix_next, uint32_t &ix_next2) {
-        int const s = e & 1, r = e % kRingA;
-        load_x(ix_next, xn);
-        ix_next2 = x_index(e + 2);
-        if (e >= 2) {                                        // stage s (TMEM columns, lo buffer) and ring slot (e-2) are free
-            mbar_wait(&bar_mma[s], unsigned(((e >> 1) - 1) & 1));
-            tc_fence_after();
-            if (0 == tid && e - 2 + kRingA < nE) fetch_a(e - 2 + kRingA);
-        }
-        // ---- X operand: split, registers -> tensor memory (lane = m, column = k) ------------------------
-        {
-            uint32_t hi[16], lo[16];
+        if (1 == cx) {
             #pragma unroll
-            for (int t = 0; t < 16; ++t) split_rn(xc[t], hi[t], lo[t]);
-            uint32_t const t0 = tmem_base + (uint32_t(32*q) << 16) + kTmemStage0 + uint32_t(s)*64 + uint32_t(16*h);
-            tmem_st16(t0, hi);
-            tmem_st16(t0 + 32, lo);
+            for (int i = 0; i < LM; ++i) exch[((g*2 + h)*LM + i)*LN + j] = __uint_as_float(d[i]);
         }
-        // ---- A operand: hi = the raw block in the ring, lo = a - trunc(a) -> shared memory ------------------
-        mbar_wait(&bar_a[r], unsigned((e / kRingA) & 1));
-        {
-            float4 const *const src = reinterpret_cast<float4 const*>(ring + size_t(r)*ABLK);
-            float4 *const dst = reinterpret_cast<float4*>(lo_mem + size_t(s)*ABLK);
+        asm volatile("bar.sync 1, %0;" :: "n"(kConvThreads) : "memory");     // converter warps only
+        if (0 == cx && has_g) {
+            float *const yp = a.y + size_t(iy)*XBLK + size_t(h)*LM*LN + j;       // plane h: 0 = Re, 1 = Im
+            float const sgn = h ? 1.f : -1.f;                                     // Yr = XrAr - XiAi ; Yi = XrAi + XiAr
             #pragma unroll
-            for (int c2 = 0; c2 < 2; ++c2) {
-                float4 v = src[tid + kTcThreads*c2];
-                v.x = lo_trunc(v.x); v.y = lo_trunc(v.y); v.z = lo_trunc(v.z); v.w = lo_trunc(v.w);
-                dst[tid + kTcThreads*c2] = v;
-            }
+            for (int i = 0; i < LM; ++i) yp[i*LN] = __uint_as_float(d[i]) + sgn*exch[((g*2 + (1 - h))*LM + i)*LN + j];
         }
-        tmem_wait_st();
-        fence_proxy_async();       // generic-proxy shared-memory writes -> visible to the tensor core
-        tc_fence_before();
-        __syncthreads();
-        if (0 == tid) {
-            tc_fence_after();
-            uint32_t const sa_hi = smem_u32(ring + size_t(r)*ABLK), sa_lo = smem_u32(lo_mem + size_t(s)*ABLK);
-            uint32_t const xa = tmem_base + kTmemStage0 + uint32_t(s)*64;
-            #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-                uint64_t const bhi = smem_desc_noswizzle(sa_hi + ks*KSB, LBO, SBO);
-                uint64_t const blo = smem_desc_noswizzle(sa_lo + ks*KSB, LBO, SBO);
-                uint32_t const first = (e > 0 || ks > 0) ? 1u : 0u;
-                // the two correction products go to their OWN accumulator: the tensor core truncates the fp32
-                // accumulator once per MMA, and 2/3 of those events would otherwise hit the large sum
-                mma_tf32_ts(tmem_base + N, xa + 32 + 8*ks, bhi, IDESC, first);   // Xlo * Ahi
-                mma_tf32_ts(tmem_base + N, xa + 8*ks,      blo, IDESC, 1u);      // Xhi * Alo
-                mma_tf32_ts(tmem_base,     xa + 8*ks,      bhi, IDESC, first);   // Xhi * Ahi
-            }
-            mma_commit(&bar_mma[s]);
-        }
-    };
-
-    if (nE > 0) {
-        float xa_[16], xb_[16];
-        uint32_t i1 = x_index(1), i2 = kNoBlock;
-        load_x(x_index(0), xa_);
-        for (int e = 0; e < nE; e += 2) {
-            step(e, xa_, xb_, i1, i2);                       // i2 := index of entry e+2
-            if (e + 1 < nE) step(e + 1, xb_, xa_, i2, i1);   // i1 := index of entry e+3
-            else break;
-        }
-        // all MMAs complete when the last commit has arrived (they retire in order)
-        mbar_wait(&bar_mma[(nE - 1) & 1], unsigned(((nE - 1) >> 1) & 1));
-        tc_fence_after();
-    }
-
-    // ---- epilogue: D -> registers, combine the four real products, store Y ---------------------------------
-    float *const exch = ring;           // [G][2][LM][LN] floats, aliases the A ring (all MMAs are done)
-    uint32_t d[32];
-    if (nE > 0) {
-        uint32_t d2[32];
-        tmem_ld32(tmem_base + (uint32_t(32*q) << 16) + uint32_t(h)*LM, d);       // D[m][(ca = h, i = 0..31)]
-        tmem_ld32(tmem_base + (uint32_t(32*q) << 16) + N + uint32_t(h)*LM, d2);  // correction terms
-        tmem_wait_ld();
-        #pragma unroll
-        for (int i = 0; i < 32; ++i) d[i] = __float_as_uint(__uint_as_float(d[i]) + __uint_as_float(d2[i]));
-    } else {
-        #pragma unroll
-        for (int i = 0; i < 32; ++i) d[i] = 0u;
-    }
-    if (1 == cx) {
-        #pragma unroll
-        for (int i = 0; i < LM; ++i) exch[((g*2 + h)*LM + i)*LN + j] = __uint_as_float(d[i]);
     }
     tc_fence_before();
     __syncthreads();
-    if (0 == cx && has_g) {
-        float *const yp = a.y + size_t(iy)*XBLK + size_t(h)*LM*LN + j;       // plane h: 0 = Re, 1 = Im
-        float const sgn = h ? 1.f : -1.f;                                     // Yr = XrAr - XiAi ; Yi = XrAi + XiAr
-        #pragma unroll
-        for (int i = 0; i < LM; ++i) yp[i*LN] = __uint_as_float(d[i]) + sgn*exch[((g*2 + (1 - h))*LM + i)*LN + j];
-    }
-    if (0 == w) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+    if (kConvWarps == w) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
 template <int LM, int LN>
