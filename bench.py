@@ -87,6 +87,24 @@ def cpu_reference_sample(lm, ln, ncols, prec, tol, maxit, repeats=1):
                        f"{ncols*ln} RHS, tol {tol:g}: one complete solve ({its} iterations, {flops*1e-9:.1f} GFLOP)")
 
 
+def reference_gpu_same_box(sp, lm, ln, prec, tol, maxit):
+    """Informational: the reference's OWN CUDA kernels (unmodified sources, nvcc -arch=sm_100, oracle/_ref) on this GPU,
+    same full-size workload, one warm-up + one timed solve.  Not the contract's reference arm (that is the CPU path)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orclib as O
+    ref = O.ref_gpu()
+    if ref is None:
+        return None
+    vA = sp.valA_host.numpy().reshape(-1); vB = sp.valB.reshape(-1)
+    out = None
+    for _ in range(2):
+        with Quiet():
+            out = ref.solve(sp.mb, lm, ln, sp.rpA, sp.ciA, vA, sp.rpX, sp.ciX, sp.rpB, sp.ciB, vB, tol, maxit, prec)
+    return {"value": out["flops"]/out["t_solve"]*1e-9, "unit": UNIT, "ms_per_solve": 1e3*out["t_solve"], "iterations": out["iterations"],
+            "status": int(out["status"]), "residual": out["residuum"],
+            "what": "unmodified reference CUDA kernels (gemmNxNf etc.) recompiled for sm_100, same GPU, same workload"}
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -281,6 +299,11 @@ def run_ours(args):
         r = cpu_reference_sample(lm, ln, ncols, prec, tol, maxit, repeats=1)
         line["cpu_baseline"] = {"value": r["flops"]/r["times"][0]*1e-9, "unit": UNIT, "cores": 1, "kind": r["kind"],
                                 "sample": r["sample"], "host_cores_available": os.cpu_count()}
+        if not args.no_ref_gpu:
+            try:
+                line["reference_gpu"] = reference_gpu_same_box(sp, lm, ln, prec, tol, maxit)
+            except Exception as e:  # informational leg only
+                line["reference_gpu"] = {"error": repr(e)[:200]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -300,7 +323,8 @@ def main():
     ap.add_argument("--ncols", type=int, default=2, help="block columns of X per GPU")
     ap.add_argument("--precision", default="c", choices=["c", "z"])
     ap.add_argument("--tol", type=float, default=1e-4)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline (and reference_gpu) legs")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the informational same-box run of the reference's CUDA kernels")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

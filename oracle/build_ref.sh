@@ -3,6 +3,9 @@
 #   cpu : reference CPU path (-DHAS_NO_CUDA, the reference's own fallback; SURVEY.md §8c recipe)
 #   gen : the reference's FD example generator (example/tfqmrgpu_generate_FD_example.cxx)
 #   gpu : reference CUDA kernels compiled for sm_100 (same-box GPU baseline; optional)
+#   callers : the reference's OWN callers, unmodified, linked against OUR libtfQMRgpu.so (drop-in evidence):
+#             example/tfqmrgpu_C_example.c -> _ref/c_example_ours ; source/bench_tfqmrgpu.cu -> _ref/bench_tfqmrgpu_ours
+#             (and bench_tfqmrgpu_ref linked against _ref/libtfqmr_ref_gpu.so for same-box comparisons)
 # Sources are compiled where they lie; nothing is copied. Outputs go to oracle/_ref/ only (git-ignored).
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -31,5 +34,25 @@ if [ "$what" = all ] || [ "$what" = gpu ]; then
         -include cstdint $INC -shared "$REF/tfQMRgpu/source/tfqmrgpu.cu" "$HERE/ref_harness.cpp" \
         -o "$OUT/libtfqmr_ref_gpu.so" -lcurand
     echo "built $OUT/libtfqmr_ref_gpu.so"
+  fi
+fi
+if [ "$what" = all ] || [ "$what" = callers ]; then
+  OURS="$HERE/../tfqmrgpu_b200/lib"
+  if [ -f "$OURS/libtfQMRgpu.so" ]; then
+    gcc -O2 -DHAS_TFQMRGPU "$REF/example/tfqmrgpu_C_example.c" -o "$OUT/c_example_ours" \
+        -L"$OURS" -ltfQMRgpu -lm -Wl,-rpath,'$ORIGIN/../../tfqmrgpu_b200/lib'
+    echo "built $OUT/c_example_ours"
+    if command -v nvcc >/dev/null; then
+      nvcc -std=c++14 -O2 -arch=sm_100 -Xcompiler=-fopenmp,-fno-tree-dce,-fno-aggressive-loop-optimizations \
+          -include cstdint $INC "$REF/tfQMRgpu/source/bench_tfqmrgpu.cu" -o "$OUT/bench_tfqmrgpu_ours" \
+          -L"$OURS" -ltfQMRgpu -Xlinker -rpath,'$ORIGIN/../../tfqmrgpu_b200/lib'
+      echo "built $OUT/bench_tfqmrgpu_ours"
+      if [ -f "$OUT/libtfqmr_ref_gpu.so" ]; then
+        nvcc -std=c++14 -O2 -arch=sm_100 -Xcompiler=-fopenmp,-fno-tree-dce,-fno-aggressive-loop-optimizations \
+            -include cstdint $INC "$REF/tfQMRgpu/source/bench_tfqmrgpu.cu" -o "$OUT/bench_tfqmrgpu_ref" \
+            -L"$OUT" -ltfqmr_ref_gpu -lcurand -Xlinker -rpath,'$ORIGIN'
+        echo "built $OUT/bench_tfqmrgpu_ref"
+      fi
+    fi
   fi
 fi

@@ -36,6 +36,17 @@ class OrcInfo(C.Structure):
                 ("last_max_bound2", C.c_double), ("last_target_bound2", C.c_double)]
 
 
+class quiet_stdout:
+    """Silence the C-level stdout chatter of the reference library (its debug printf is always on)."""
+    def __enter__(self):
+        import sys
+        sys.stdout.flush()
+        self.saved = os.dup(1); self.null = os.open(os.devnull, os.O_WRONLY); os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1); os.close(self.saved); os.close(self.null)
+
+
 _oracle = None
 
 

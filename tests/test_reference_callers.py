@@ -1,0 +1,88 @@
+"""Drop-in evidence on the GPU box: the reference's OWN callers, compiled unmodified from /root/reference in the
+build container (oracle/build_ref.sh callers|gpu; the binaries travel in oracle/_ref/, nothing here reads
+/root/reference) and linked against OUR libtfQMRgpu.so, plus solve parity against the reference's own CUDA
+kernels (oracle/_ref/libtfqmr_ref_gpu.so, nvcc -arch=sm_100 of the unmodified sources) on the same GPU with the
+same cuRAND shadow vector."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import orclib as O
+from cases import golden_cases
+from tfqmrgpu_b200 import api, problems as P, _lib as L
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _have(name):
+    return os.path.exists(os.path.join(REFDIR, name))
+
+
+@pytest.mark.skipif(not _have("c_example_ours"), reason="oracle/_ref/c_example_ours not built")
+def test_reference_c_example_runs_against_our_library():
+    """example/tfqmrgpu_C_example.c (args of SURVEY 8c) through tfqmrgpu_bsrsv_z of OUR library."""
+    out = subprocess.run([os.path.join(REFDIR, "c_example_ours"), "6", "4", "4", ".125", ".5", ".125", "100", "1e-6"],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    m = re.search(r"tfQMRgpu converged to ([0-9.e+-]+) in (\d+) iterations", out.stdout)
+    assert m, out.stdout
+    assert float(m.group(1)) <= 1e-6 and 3 <= int(m.group(2)) <= 40
+
+
+@pytest.mark.skipif(not (_have("bench_tfqmrgpu_ours") and _have("bench_tfqmrgpu_ref")), reason="reference bench not built")
+def test_reference_bench_harness_same_output_with_both_libraries():
+    """`bench_tfqmrgpu tfQMR FD_problem.xml z` (README :61-63): the reference's harness linked against our library and
+    against the reference's own CUDA build must report the same solution statistics (the file's reference X is all
+    zeros, so maxdev/avgdev are max|X| and mean|X|)."""
+    xml = os.path.join(ROOT, "tests", "golden", "FD_problem.xml")
+    vals = {}
+    for which in ("ours", "ref"):
+        out = subprocess.run([os.path.join(REFDIR, "bench_tfqmrgpu_" + which), "tfQMR", xml, "z"],
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        m = re.search(r"# GPU maxdev ([0-9.e+-]+) avgdev ([0-9.e+-]+)", out.stdout)
+        assert m, out.stdout[-2000:]
+        vals[which] = (float(m.group(1)), float(m.group(2)))
+    assert abs(vals["ours"][0] - vals["ref"][0]) <= 1e-8*vals["ref"][0]
+    assert abs(vals["ours"][1] - vals["ref"][1]) <= 1e-8*vals["ref"][1]
+
+
+CASES = golden_cases()
+
+
+@pytest.mark.skipif(not _have("libtfqmr_ref_gpu.so"), reason="oracle/_ref/libtfqmr_ref_gpu.so not built")
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_solve_vs_reference_cuda_build_same_gpu(case):
+    """Same inputs, same cuRAND v3 (both draw XORWOW seed 1234 in the caller's block order): status and iteration
+    count identical, residual and X within the stated tolerance, flop count identical when iterations agree."""
+    name, prob, prec, tol, maxit, tA, tB = case
+    dt = np.float64 if prec == "z" else np.float32
+    vA = P.interleave(prob.A.val, dt); vB = P.interleave(prob.B.val, dt)
+    ref = O.ref_gpu()
+    with O.quiet_stdout():
+        r = ref.solve(prob.mb, prob.lm, prob.ln, prob.A.rowptr, prob.A.colind, vA, prob.X.rowptr, prob.X.colind,
+                      prob.B.rowptr, prob.B.colind, vB, tol, maxit, prec, transA=tA, trans_b=tB)
+    h = api.Handle()
+    pl = api.BsrsvPlan(h, prob.mb, prob.A.rowptr, prob.A.colind, prob.X.rowptr, prob.X.colind, prob.B.rowptr, prob.B.colind)
+    pl.buffer_size_for(prob.lm, prob.ln, prec); pl.set_buffer()
+    assert np.array_equal(pl.get_v3().reshape(-1), r["v3"])          # identical shadow vector
+    pl.set_matrix("A", vA, tA); pl.set_matrix("B", vB, tB)
+    st = pl.solve(tol, maxit)
+    info = pl.info()
+    X = pl.get_matrix("X", "n", L.LAYOUT_RRRRIIII).reshape(pl.nnzbX, 2, prob.lm, prob.ln)
+    lists = pl.plan_lists()
+    pl.close(); h.close()
+    for k in ("starts", "pairs", "subset", "colindx"):
+        assert np.array_equal(lists[k], r["lists"][k]), k
+    assert st == r["status"]
+    assert abs(info["iterations"] - r["iterations"]) <= 1
+    if info["iterations"] == r["iterations"]:
+        assert info["flops"] == r["flops"]
+    assert info["residuum"] <= tol and r["residuum"] <= tol
+    scale = np.abs(r["X"]).max()
+    assert np.abs(X - r["X"]).max() <= (10 if prec == "z" else 50)*tol*scale
