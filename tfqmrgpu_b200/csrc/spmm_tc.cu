@@ -156,11 +156,20 @@ spmm_tc_kernel(TcArgs const a)
     // B operand (the A block) in shared memory: K-major, no swizzle, [k/4][n][k%4] - the layout setMatrix('A') stores
     // in HBM for these plans (layout.cu), so one bulk copy per block lands it ready for the MMA.
     // (MN-major TF32 operands return zeros on sm_100a - measured, see DESIGN.md.)
-    constexpr uint32_t KSB = N*32;        // bytes of one k-step: [2 k-quads][N rows][4 k]
-    constexpr uint32_t LBO = N*16;
+    // A ring slot: per k-quad a slab [hi: N rows x 16 B][lo: N rows x 16 B].  hi arrives by bulk copy (one copy per
+    // k-quad slab), lo is written next to it, so ONE descriptor with 2N rows covers [Ahi ; Alo]:
+    //   Xhi * [Ahi ; Alo]  -> columns [0,N) (main sum) and [N,2N) (correction sum) of the accumulator, one MMA of N' = 2N
+    //   Xlo *  Ahi         -> columns [N,2N), one MMA of N' = N
+    // i.e. 2 MMAs per k-step instead of 3 (the per-instruction overhead dominates at these small N).
+    constexpr uint32_t SLAB = N*16;       // bytes of one hi (or lo) k-quad slab
+    constexpr uint32_t KSB = 4*SLAB;      // bytes of one k-step: 2 k-quads x (hi + lo)
+    constexpr uint32_t LBO = 2*SLAB;      // between the two k-quads of a k-step
     constexpr uint32_t SBO = 128;
-    // instruction descriptor: D fp32, A/B TF32, both K-major, N, M = 128
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+    constexpr uint32_t SLOT = 2*ABLK*4;   // bytes of a ring slot (hi + lo)
+    // instruction descriptors: D fp32, A/B TF32, both K-major, M = 128, N' = 2N and N
+    constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(128 >> 4) << 24);
+    constexpr uint32_t IDESC_2N = IDESC_BASE | (uint32_t((2*N) >> 3) << 17);
+    constexpr uint32_t IDESC_N  = IDESC_BASE | (uint32_t(N >> 3) << 17);
 
     if (a.expect >= 0 && a.ctl->state != a.expect) return; // device-resident solver control
 
@@ -170,8 +179,7 @@ spmm_tc_kernel(TcArgs const a)
     uint64_t *const bar_a     = bar_mma + 4;                                // [kRingA] raw A block has landed
     uint32_t *const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 128);
     uint32_t *const s_y = reinterpret_cast<uint32_t*>(smem_raw + 160);      // [G]
-    float *const ring   = reinterpret_cast<float*>(smem_raw + 1024);        // [kRingA][ABLK] raw A = hi operand
-    float *const lo_mem = ring + size_t(kRingA)*ABLK;                       // [2][ABLK]      lo operand
+    unsigned char *const ring = smem_raw + 1024;                            // [kRingA][SLOT] A operands, hi and lo slabs interleaved
 
     int const tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     uint32_t const u = blockIdx.x;
@@ -202,10 +210,13 @@ spmm_tc_kernel(TcArgs const a)
             int const r = e % kRingA;
             uint32_t const ia = a.ent_a[e0 + e];
             mbar_expect_tx(&bar_a[r], unsigned(ABLK*sizeof(float)));
-            bulk_g2s(ring + size_t(r)*ABLK, a.A + size_t(ia)*ABLK, unsigned(ABLK*sizeof(float)), &bar_a[r]);
+            unsigned char const *src = reinterpret_cast<unsigned char const*>(a.A + size_t(ia)*ABLK);
+            #pragma unroll
+            for (int kq = 0; kq < LM/4; ++kq)      // one k-quad slab each, leaving room for the lo slab behind it
+                bulk_g2s(ring + size_t(r)*SLOT + size_t(kq)*2*SLAB, src + size_t(kq)*SLAB, SLAB, &bar_a[r]);
         };
         if (leader) for (int e = 0; e < kRingA && e < nE; ++e) fetch_a(e);
-        uint32_t const ring_u32 = smem_u32(ring), lo_u32 = smem_u32(lo_mem);
+        uint32_t const ring_u32 = smem_u32(ring);
         for (int e = 0; e < nE; ++e) {
             int const s = e & 1, r = e % kRingA;
             if (e >= 2 && e - 2 + kRingA < nE) {                // ring slot of entry e-2 is free once its MMAs completed
@@ -215,18 +226,16 @@ spmm_tc_kernel(TcArgs const a)
             mbar_wait(&bar_ready[s], unsigned((e >> 1) & 1));   // X in TMEM, lo in shared memory (and the raw A landed)
             tc_fence_after();
             if (leader) {
-                uint32_t const sa_hi = ring_u32 + uint32_t(r)*ABLK*4, sa_lo = lo_u32 + uint32_t(s)*ABLK*4;
+                uint32_t const sa = ring_u32 + uint32_t(r)*SLOT;
                 uint32_t const xa = tmem_base + kTmemStage0 + uint32_t(s)*64;
                 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
-                    uint64_t const bhi = smem_desc_noswizzle(sa_hi + ks*KSB, LBO, SBO);
-                    uint64_t const blo = smem_desc_noswizzle(sa_lo + ks*KSB, LBO, SBO);
+                    uint64_t const b = smem_desc_noswizzle(sa + ks*KSB, LBO, SBO);
                     uint32_t const first = (e > 0 || ks > 0) ? 1u : 0u;
-                    // the two correction products go to their OWN accumulator: the tensor core truncates the fp32
-                    // accumulator once per MMA, and 2/3 of those events would otherwise hit the large sum
-                    mma_tf32_ts(tmem_base + N, xa + 32 + 8*ks, bhi, IDESC, first);   // Xlo * Ahi
-                    mma_tf32_ts(tmem_base + N, xa + 8*ks,      blo, IDESC, 1u);      // Xhi * Alo
-                    mma_tf32_ts(tmem_base,     xa + 8*ks,      bhi, IDESC, first);   // Xhi * Ahi
+                    // main sum in columns [0,N), correction sum in [N,2N): the tensor core truncates the fp32 accumulator
+                    // once per MMA, so the small correction products must not share the large sum's accumulator
+                    mma_tf32_ts(tmem_base,     xa + 8*ks,      b, IDESC_2N, first);   // Xhi * [Ahi ; Alo]
+                    mma_tf32_ts(tmem_base + N, xa + 32 + 8*ks, b, IDESC_N,  1u);      // Xlo * Ahi
                 }
                 mma_commit(&bar_mma[s]);
             }
@@ -269,13 +278,14 @@ spmm_tc_kernel(TcArgs const a)
             // ---- A operand: hi = the raw block in the ring, lo = a - trunc(a) -> shared memory ------------------
             mbar_wait(&bar_a[r], unsigned((e / kRingA) & 1));
             {
-                float4 const *const src = reinterpret_cast<float4 const*>(ring + size_t(r)*ABLK);
-                float4 *const dst = reinterpret_cast<float4*>(lo_mem + size_t(s)*ABLK);
+                unsigned char *const slot = ring + size_t(r)*SLOT;
                 #pragma unroll
                 for (int c2 = 0; c2 < 2; ++c2) {
-                    float4 v = src[tid + kConvThreads*c2];
+                    int const c = tid + kConvThreads*c2;          // (k-quad, n) chunk of 4 k values
+                    int const kq = c / N, n = c % N;
+                    float4 v = *reinterpret_cast<float4 const*>(slot + size_t(kq)*2*SLAB + size_t(n)*16);
                     v.x = lo_trunc(v.x); v.y = lo_trunc(v.y); v.z = lo_trunc(v.z); v.w = lo_trunc(v.w);
-                    dst[tid + kConvThreads*c2] = v;
+                    *reinterpret_cast<float4*>(slot + size_t(kq)*2*SLAB + SLAB + size_t(n)*16) = v;
                 }
             }
             tmem_wait_st();
@@ -300,7 +310,7 @@ spmm_tc_kernel(TcArgs const a)
         }
 
         // ---- epilogue: D -> registers, combine the four real products, store Y ---------------------------------
-        float *const exch = ring;           // [G][2][LM][LN] floats, aliases the A ring (all copies and MMAs are done)
+        float *const exch = reinterpret_cast<float*>(ring);   // [G][2][LM][LN] floats, aliases the A ring (all copies and MMAs are done)
         uint32_t d[32];
         if (nE > 0) {
             uint32_t d2[32];
@@ -333,7 +343,7 @@ spmm_tc_kernel(TcArgs const a)
 template <int LM, int LN>
 tfqmrgpuStatus_t launch_tc(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream)
 {
-    constexpr size_t smem = 1024 + (kRingA + 2)*size_t(2*LM*LM)*sizeof(float) + 1024; // barriers + A ring + two lo stages
+    constexpr size_t smem = 1024 + kRingA*2*size_t(2*LM*LM)*sizeof(float) + 1024; // barriers + A ring (hi and lo slabs)
     // two CTAs per SM (two 256-column TMEM allocations): pad the request so that a third CTA can never be resident
     constexpr size_t smem_req = (smem < 80*1024) ? 80*1024 : smem;
     auto kernel = spmm_tc_kernel<LM, LN>;
