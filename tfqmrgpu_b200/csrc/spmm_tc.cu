@@ -28,6 +28,7 @@
 // of entry e+1 are in flight while entry e is split, and two CTAs per SM overlap each other's
 // prologue/epilogue.
 #include "tfq_internal.hpp"
+#include <algorithm>
 
 namespace tfq {
 
@@ -41,7 +42,7 @@ constexpr uint32_t kTmemStage0 = 128;
 struct TcArgs {
     float *y; float const *x; float const *A;
     uint32_t const *unit_e0, *unit_y, *ent_a, *ent_x;
-    Control const *ctl; int expect; int gstride;
+    Control const *ctl; int expect; int gstride; uint32_t nUnits;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(void const *p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -56,6 +57,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, void const *src_gmem, unsigned bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(uint64_t *bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -182,10 +186,19 @@ spmm_tc_kernel(TcArgs const a)
     unsigned char *const ring = smem_raw + 1024;                            // [kRingA][SLOT] A operands, hi and lo slabs interleaved
 
     int const tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    uint32_t const u = blockIdx.x;
+    int const gs = a.gstride;
+
+    if (kConvWarps == w) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t const tmem_base = *tmem_slot;
+
+    // persistent: two resident CTAs per SM walk the units; TMEM is allocated once, the barriers are re-armed per unit
+    // (a gated-off launch of this kernel then costs a handful of CTAs instead of one per unit)
+    for (uint32_t u = blockIdx.x; u < a.nUnits; u += gridDim.x) {
     uint32_t const e0 = a.unit_e0[u];
     int const nE = int(a.unit_e0[u + 1] - e0);
-    int const gs = a.gstride;
 
     if (tid < G) s_y[tid] = (tid < gs) ? a.unit_y[size_t(u)*gs + tid] : kNoBlock;
     if (0 == tid) {
@@ -195,11 +208,7 @@ spmm_tc_kernel(TcArgs const a)
         for (int r = 0; r < kRingA; ++r) mbar_init(&bar_a[r], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (kConvWarps == w) tmem_alloc(tmem_slot, kTmemCols);
-    tc_fence_before();
     __syncthreads();
-    tc_fence_after();
-    uint32_t const tmem_base = *tmem_slot;
 
     if (kConvWarps == w) {
         // ================= issuer warp: bulk copies of the A blocks and the MMAs =====================================
@@ -336,9 +345,19 @@ spmm_tc_kernel(TcArgs const a)
         }
     }
     tc_fence_before();
+    __syncthreads();          // everyone is done with this unit's accumulator, ring and barriers
+    tc_fence_after();
+    if (0 == tid) {
+        mbar_inval(&bar_mma[0]); mbar_inval(&bar_mma[1]); mbar_inval(&bar_ready[0]); mbar_inval(&bar_ready[1]);
+        #pragma unroll
+        for (int r = 0; r < kRingA; ++r) mbar_inval(&bar_a[r]);
+    }
+    } // units
+    tc_fence_before();
     __syncthreads();
     if (kConvWarps == w) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
+
 
 template <int LM, int LN>
 tfqmrgpuStatus_t launch_tc(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream)
@@ -355,8 +374,11 @@ tfqmrgpuStatus_t launch_tc(Plan const &p, void *y, void const *x, int expect, cu
     TcArgs a;
     a.y = static_cast<float*>(y); a.x = static_cast<float const*>(x); a.A = ws<float const>(p, p.off_A);
     a.unit_e0 = p.d_unit_e0; a.unit_y = p.d_unit_y; a.ent_a = p.d_ent_a; a.ent_x = p.d_ent_x;
-    a.ctl = ws<Control const>(p, p.off_ctl); a.expect = expect; a.gstride = int(p.gmax);
-    if (p.nUnits > 0) kernel<<<p.nUnits, kTcThreads, smem_req, stream>>>(a);
+    a.ctl = ws<Control const>(p, p.off_ctl); a.expect = expect; a.gstride = int(p.gmax); a.nUnits = p.nUnits;
+    static int num_sms = 0;
+    if (0 == num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    uint32_t const grid = std::min<uint32_t>(p.nUnits, 2u*uint32_t(num_sms));   // two CTAs per SM (TMEM: 2 x 256 columns)
+    if (grid > 0) kernel<<<grid, kTcThreads, smem_req, stream>>>(a);
     TFQ_CUDA(cudaGetLastError());
     return TFQMRGPU_STATUS_SUCCESS;
 }
