@@ -43,9 +43,9 @@ SAMPLE_N = 6
 DEFAULT_TOL = 1e-3
 
 
-def workload_name(n, lm, ln, ncols, prec, tol=1e-3):
+def workload_name(n, lm, ln, ncols, prec, tol=1e-3, sigma=8.0):
     return (f"stencil27 n={n}^3={n**3} block rows, {lm}x{ln} complex {'fp64' if prec == 'z' else 'fp32'} blocks, "
-            f"{ncols*ln} RHS columns per GPU, sigma=8, tol={tol:g}")
+            f"{ncols*ln} RHS columns per GPU, sigma={sigma:g}, tol={tol:g}")
 
 
 class Quiet:
@@ -186,7 +186,7 @@ def run_ours(args):
     es = 8 if prec == "z" else 4
 
     # this rank's shard: block columns [rank*ncols, (rank+1)*ncols) of a world*ncols-column problem, A replicated
-    sp = synthetic.Stencil27(n, lm, ln, ncols, sigma=8.0, dtype=dt, device=dev, col0=rank*ncols, ncols_global=world*ncols)
+    sp = synthetic.Stencil27(n, lm, ln, ncols, sigma=args.sigma, dtype=dt, device=dev, col0=rank*ncols, ncols_global=world*ncols)
     h = api.Handle(torch.cuda.current_stream(dev).cuda_stream)
     pl = api.BsrsvPlan(h, sp.mb, sp.rpA, sp.ciA, sp.rpX, sp.ciX, sp.rpB, sp.ciB)
     nbytes = pl.buffer_size_for(lm, ln, prec)
@@ -290,7 +290,7 @@ def run_ours(args):
             "metric": METRIC, "value": total_flops/(ms*1e-3)*1e-9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms/args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64" if prec == "z" else "f32", "data": "synthetic",
-            "config": {"workload": workload_name(n, lm, ln, ncols, prec, tol), "parallelism": f"rhs-column sharding x{world}, A replicated",
+            "config": {"workload": workload_name(n, lm, ln, ncols, prec, tol, args.sigma), "parallelism": f"rhs-column sharding x{world}, A replicated",
                        "l2": "working set 12 GB per GPU >> 126 MB L2, no flush needed",
                        "iterations_per_solve": iters/args.steps, "iterations_per_solve_min_max_over_ranks": [iters_min, iters_max],
                        "residual_reached": last["residuum"], "status": int(statuses[-1]), "worst_status_over_ranks": worst_status,
@@ -330,6 +330,7 @@ def main():
     ap.add_argument("--ncols", type=int, default=2, help="block columns of X per GPU")
     ap.add_argument("--precision", default="c", choices=["c", "z"])
     ap.add_argument("--tol", type=float, default=DEFAULT_TOL)
+    ap.add_argument("--sigma", type=float, default=8.0, help="diagonal shift of the stencil operator (8: fp32 config; 1: fp64 configs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline (and reference_gpu) legs")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the informational same-box run of the reference's CUDA kernels")
     args = ap.parse_args()
