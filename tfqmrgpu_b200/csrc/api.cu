@@ -219,6 +219,7 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_setBuffer(tfqmrgpuHandle_t handle, tfqmrgpuBsrsv
     if (size_t(pBuffer) & 255) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);  // 2^TFQMRGPU_MEMORY_ALIGNMENT
     cudaStream_t const stream = static_cast<Handle*>(handle)->stream;
     p.pBuffer = static_cast<char*>(pBuffer);
+    plan_drop_graph(p);               // the captured iteration body holds pointers into the old workspace
     TFQ_CUDA(cudaMemsetAsync(p.pBuffer + p.off_zero, 0, p.bufferBytes - 256 - p.off_zero, stream)); // zero block, scalars, tickets, control
     tfqmrgpuStatus_t const st = fill_v3(p, stream);
     if (TFQMRGPU_STATUS_SUCCESS != st) return st;

@@ -304,7 +304,12 @@ tfqmrgpuStatus_t plan_analyse(Plan &p, cudaStream_t stream,
 }
 
 // ------------------------------------------------------------------------------------------------
+void plan_drop_graph(Plan &p) {
+    if (p.body_exec) { cudaGraphExecDestroy(p.body_exec); p.body_exec = nullptr; }
+}
+
 static void free_configured(Plan &p) {
+    plan_drop_graph(p);
     cudaFree(p.d_tiles); p.d_tiles = nullptr;
     cudaFree(p.d_coltile); p.d_coltile = nullptr;
     cudaFree(p.d_unit_e0); p.d_unit_e0 = nullptr;
@@ -320,6 +325,7 @@ void plan_release(Plan &p) {
     if (p.h_ctl) cudaFreeHost(p.h_ctl);
     for (auto &e : p.ev) if (e) cudaEventDestroy(e);
     for (auto &e : p.prof_ev) if (e) cudaEventDestroy(e);
+    if (p.capture_stream) cudaStreamDestroy(p.capture_stream);
 }
 
 tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, char precision)

@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace tfq {
 
@@ -19,6 +20,65 @@ namespace {
 constexpr int kAhead = 3;      // iteration bodies the host may run ahead of the last control read-back
 constexpr int kRing = 6;       // read-back slots; slot 6 = final state, slot 7 = upload staging
 }
+
+namespace {
+constexpr int kBodyKernels = 11;
+
+// one tfQMR iteration (core.hxx:189-233) followed by the residual probe (core.hxx:263-304); every kernel checks the
+// device-resident state first: the iteration kernels run only in state RUN, the probe kernels only in state PROBE
+// (events: nullptr, or four events recorded around the two A*v6 products when profiling)
+tfqmrgpuStatus_t enqueue_body(Plan &p, cudaStream_t stream, cudaEvent_t const *events)
+{
+    void *const v1 = p.pBuffer + p.off_v[1], *const v6 = p.pBuffer + p.off_v[6];
+    void *const v8 = p.pBuffer + p.off_v[8], *const v9 = p.pBuffer + p.off_v[9];
+    tfqmrgpuStatus_t st;
+#define TFQ_DO(call) do { st = (call); if (TFQMRGPU_STATUS_SUCCESS != st) return st; } while (0)
+    TFQ_DO(launch_vecop(p, OP_K1, stream));
+    if (events) TFQ_CUDA(cudaEventRecord(events[0], stream));
+    TFQ_DO(launch_spmm(p, v9, v6, STATE_RUN, stream));                 // v9 := A*v6     (core.hxx:198)
+    if (events) TFQ_CUDA(cudaEventRecord(events[1], stream));
+    TFQ_DO(launch_vecop(p, OP_E1, stream));
+    TFQ_DO(launch_vecop(p, OP_K2, stream));
+    TFQ_DO(launch_vecop(p, OP_K3, stream));
+    if (events) TFQ_CUDA(cudaEventRecord(events[2], stream));
+    TFQ_DO(launch_spmm(p, v8, v6, STATE_RUN, stream));                 // v8 := A*v6     (core.hxx:224)
+    if (events) TFQ_CUDA(cudaEventRecord(events[3], stream));
+    TFQ_DO(launch_vecop(p, OP_E2, stream));
+    TFQ_DO(launch_vecop(p, OP_K4, stream));
+    TFQ_DO(launch_spmm(p, v9, v1, STATE_PROBE, stream));               // v9 := A*v1     (core.hxx:265)
+    TFQ_DO(launch_add_rhs(p, v9, -1.0, STATE_PROBE, stream));          // v9 -= b        (core.hxx:267)
+    TFQ_DO(launch_vecop(p, OP_N3, stream));
+#undef TFQ_DO
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+// capture the body once into a CUDA graph: one launch per iteration instead of eleven (small systems such as the
+// reference's FD example are bound by launch latency).  The legacy default stream cannot be captured, so the capture
+// runs on a private stream and the instantiated graph is launched into the caller's stream.
+tfqmrgpuStatus_t build_body_graph(Plan &p)
+{
+    if (nullptr == p.capture_stream) TFQ_CUDA(cudaStreamCreateWithFlags(&p.capture_stream, cudaStreamNonBlocking));
+    TFQ_CUDA(cudaStreamBeginCapture(p.capture_stream, cudaStreamCaptureModeThreadLocal));
+    tfqmrgpuStatus_t const st = enqueue_body(p, p.capture_stream, nullptr);
+    cudaGraph_t graph = nullptr;
+    cudaError_t const e = cudaStreamEndCapture(p.capture_stream, &graph);
+    if (TFQMRGPU_STATUS_SUCCESS != st || cudaSuccess != e || nullptr == graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return (TFQMRGPU_STATUS_SUCCESS != st) ? st : TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED);
+    }
+    cudaError_t const e2 = cudaGraphInstantiate(&p.body_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    TFQ_CUDA(e2);
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+bool graphs_enabled() {
+    static int on = -1;
+    if (on < 0) { char const *e = std::getenv("TFQMRGPU_GRAPH"); on = (e && '0' == e[0]) ? 0 : 1; }
+    return 1 == on;
+}
+} // namespace
 
 tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIterations)
 {
@@ -43,6 +103,11 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
     }
     auto mark = [&](int which) { return p.profile ? cudaEventRecord(p.prof_ev[which], stream) : cudaSuccess; };
     TFQ_CUDA(mark(0));
+    bool const use_graph = graphs_enabled() && !p.profile && maxIterations > 0;
+    if (use_graph && nullptr == p.body_exec) {
+        tfqmrgpuStatus_t const gst = build_body_graph(p);
+        if (TFQMRGPU_STATUS_SUCCESS != gst) return gst;
+    }
 
     // ---- initial state (core.hxx:114-131,170-174) ----------------------------------------------------
     Control &c0 = p.h_ctl[7];
@@ -73,9 +138,6 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
         std::printf("# norms of B within [%g, %g]\n", std::sqrt(mn), std::sqrt(mx));
     }
 
-    void *const v1 = p.pBuffer + p.off_v[1], *const v6 = p.pBuffer + p.off_v[6];
-    void *const v8 = p.pBuffer + p.off_v[8], *const v9 = p.pBuffer + p.off_v[9];
-
     int bodies = 0;
     for (int i = 0; i < maxIterations; ++i) {
         if (i >= kAhead) {
@@ -83,24 +145,15 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
             TFQ_CUDA(cudaEventSynchronize(p.ev[slot]));
             if (STATE_DONE == p.h_ctl[slot].state) break;
         }
-        // ---- one tfQMR iteration (core.hxx:189-233); all kernels are no-ops unless state == RUN ------
-        bool const prof = p.profile && (i < kProfBodies);
-        TFQ_DO(launch_vecop(p, OP_K1, stream));
-        if (prof) TFQ_CUDA(mark(2 + 4*i));
-        TFQ_DO(launch_spmm(p, v9, v6, STATE_RUN, stream));                 // v9 := A*v6     (core.hxx:198)
-        if (prof) TFQ_CUDA(mark(3 + 4*i));
-        TFQ_DO(launch_vecop(p, OP_E1, stream));
-        TFQ_DO(launch_vecop(p, OP_K2, stream));
-        TFQ_DO(launch_vecop(p, OP_K3, stream));
-        if (prof) TFQ_CUDA(mark(4 + 4*i));
-        TFQ_DO(launch_spmm(p, v8, v6, STATE_RUN, stream));                 // v8 := A*v6     (core.hxx:224)
-        if (prof) TFQ_CUDA(mark(5 + 4*i));
-        TFQ_DO(launch_vecop(p, OP_E2, stream));
-        TFQ_DO(launch_vecop(p, OP_K4, stream));
-        // ---- residual probe (core.hxx:263-304); no-ops unless the device asked for it ---------------
-        TFQ_DO(launch_spmm(p, v9, v1, STATE_PROBE, stream));               // v9 := A*v1     (core.hxx:265)
-        TFQ_DO(launch_add_rhs(p, v9, -1.0, STATE_PROBE, stream));          // v9 -= b        (core.hxx:267)
-        TFQ_DO(launch_vecop(p, OP_N3, stream));
+        if (use_graph) {
+            TFQ_CUDA(cudaGraphLaunch(p.body_exec, stream));
+            launches += kBodyKernels;
+        } else {
+            bool const prof = p.profile && (i < kProfBodies);
+            st = enqueue_body(p, stream, prof ? &p.prof_ev[2 + 4*i] : nullptr);
+            if (TFQMRGPU_STATUS_SUCCESS != st) return st;
+            launches += kBodyKernels;
+        }
         int const slot = i % kRing;
         TFQ_CUDA(cudaMemcpyAsync(&p.h_ctl[slot], d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, stream));
         TFQ_CUDA(cudaEventRecord(p.ev[slot], stream));

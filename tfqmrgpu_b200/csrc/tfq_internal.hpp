@@ -96,6 +96,10 @@ struct Plan {
     Control *h_ctl = nullptr;         // pinned ring for control read-backs
     cudaEvent_t ev[8] = {nullptr};
     bool v3_ready = false, solved = false;
+    // one tfQMR iteration body (8 iteration kernels + 3 probe kernels) as an instantiated CUDA graph; rebuilt when the
+    // workspace or the block configuration changes
+    cudaGraphExec_t body_exec = nullptr;
+    cudaStream_t    capture_stream = nullptr;
 
     // ---- stats (tfqmrgpu_plan.hxx:41-45) -------------------------------------------------------
     double residuum_reached = 0, flops_performed = -1, flops_performed_all = 0;
@@ -113,6 +117,7 @@ tfqmrgpuStatus_t plan_analyse(Plan &p, cudaStream_t stream,
     int32_t const *rpB, int32_t const *ciB, int echo);
 tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, char precision); // tiles, units, offsets
 void plan_release(Plan &p);
+void plan_drop_graph(Plan &p);   // forget the captured iteration body
 
 // ---- kernels' host launchers --------------------------------------------------------------------
 // block-sparse product y = A*x on storage-ordered vectors; gate: run only if ctl->state == expect (expect < 0: always)

@@ -417,14 +417,25 @@ vec_kernel(VecArgs<real_t> const a)
         m1 += __ldcg(&a.colmon[size_t(cc)*4 + 1]);
         m2 += __ldcg(&a.colmon[size_t(cc)*4 + 2]);
     }
+    // block reduction (max, sum, sum) in a fixed order: shared memory, then the first warp (always complete: blockDim >= 224)
+    // strides over the entries and finishes with shuffles.  (A serial loop of one thread over blockDim entries cost ~10 us.)
     __syncthreads();
     red[tid] = m0; red[blockDim.x + tid] = m1; red[2*blockDim.x + tid] = m2;
     __syncthreads();
+    if (tid >= 32) return;
+    m0 = 0; m1 = 0; m2 = 0;
+    for (unsigned q = tid; q < blockDim.x; q += 32) {
+        double const x0 = red[q];
+        m0 = (m0 < x0) ? x0 : m0; m1 += red[blockDim.x + q]; m2 += red[2*blockDim.x + q];
+    }
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double const x0 = __shfl_down_sync(0xffffffffu, m0, off);
+        m0 = (m0 < x0) ? x0 : m0;
+        m1 += __shfl_down_sync(0xffffffffu, m1, off);
+        m2 += __shfl_down_sync(0xffffffffu, m2, off);
+    }
     if (0 == tid) {
-        for (unsigned q = 1; q < blockDim.x; ++q) {
-            double const x0 = red[q];
-            m0 = (m0 < x0) ? x0 : m0; m1 += red[blockDim.x + q]; m2 += red[2*blockDim.x + q];
-        }
         Control &ctl = *a.ctl;
         ctl.cols_done = 0;
         if (OP == OP_K4) {
