@@ -4,6 +4,7 @@
 #include <curand.h>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <new>
 
 namespace tfq {
@@ -258,8 +259,33 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_setMatrix(tfqmrgpuHandle_t handle, tfqmrgpuBsrsv
     if (('z' == lower(precision)) != is_double) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, precision); // tfqmrgpu.cu:538-542
     if ('a' == v) {
         char *const dst = p.pBuffer + p.off_A;
-        TFQ_CUDA(cudaMemcpyAsync(dst, val, size_t(nnzb)*2*p.LM*p.LM*s, cudaMemcpyHostToDevice, stream));
-        return convert_inplace(p, dst, nnzb, p.LM, p.LM, is_double, layout, trans, scal_imag, stream, p.use_tc);
+        size_t const blockBytes = 2*size_t(p.LM)*p.LM*s, bytes = size_t(nnzb)*blockBytes;
+        size_t const chunkBytes = size_t(256) << 20;
+        if (bytes <= chunkBytes) {
+            TFQ_CUDA(cudaMemcpyAsync(dst, val, bytes, cudaMemcpyHostToDevice, stream));
+            return convert_inplace(p, dst, nnzb, p.LM, p.LM, is_double, layout, trans, scal_imag, stream, p.use_tc);
+        }
+        // large operator: upload in chunks on a copy stream while the layout kernel converts the previous chunk on the
+        // caller's stream (the conversion then hides completely behind the PCIe transfer)
+        if (nullptr == p.copy_stream) TFQ_CUDA(cudaStreamCreateWithFlags(&p.copy_stream, cudaStreamNonBlocking));
+        cudaEvent_t ev;
+        TFQ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        TFQ_CUDA(cudaEventRecord(ev, stream));                   // earlier work on the caller's stream may still read A
+        TFQ_CUDA(cudaStreamWaitEvent(p.copy_stream, ev, 0));
+        TFQ_CUDA(cudaEventDestroy(ev));
+        uint32_t const blocksPerChunk = uint32_t(chunkBytes/blockBytes);
+        tfqmrgpuStatus_t cst = TFQMRGPU_STATUS_SUCCESS;
+        for (uint32_t b0 = 0; b0 < nnzb && TFQMRGPU_STATUS_SUCCESS == cst; b0 += blocksPerChunk) {
+            uint32_t const nb = std::min(blocksPerChunk, nnzb - b0);
+            size_t const off = size_t(b0)*blockBytes;
+            TFQ_CUDA(cudaMemcpyAsync(dst + off, static_cast<char const*>(val) + off, size_t(nb)*blockBytes, cudaMemcpyHostToDevice, p.copy_stream));
+            TFQ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            TFQ_CUDA(cudaEventRecord(ev, p.copy_stream));
+            TFQ_CUDA(cudaStreamWaitEvent(stream, ev, 0));
+            TFQ_CUDA(cudaEventDestroy(ev));                      // released once the event has completed
+            cst = convert_inplace(p, dst + off, nb, p.LM, p.LM, is_double, layout, trans, scal_imag, stream, p.use_tc);
+        }
+        return cst;
     }
     if ('b' == v) {
         char *const dst = p.pBuffer + p.off_B;

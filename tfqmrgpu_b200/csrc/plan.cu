@@ -326,6 +326,7 @@ void plan_release(Plan &p) {
     for (auto &e : p.ev) if (e) cudaEventDestroy(e);
     for (auto &e : p.prof_ev) if (e) cudaEventDestroy(e);
     if (p.capture_stream) cudaStreamDestroy(p.capture_stream);
+    if (p.copy_stream) cudaStreamDestroy(p.copy_stream);
 }
 
 tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, char precision)

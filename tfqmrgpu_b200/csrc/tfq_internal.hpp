@@ -100,6 +100,7 @@ struct Plan {
     // workspace or the block configuration changes
     cudaGraphExec_t body_exec = nullptr;
     cudaStream_t    capture_stream = nullptr;
+    cudaStream_t    copy_stream = nullptr;     // uploads of large operands, overlapped chunk-wise with their layout conversion
 
     // ---- stats (tfqmrgpu_plan.hxx:41-45) -------------------------------------------------------
     double residuum_reached = 0, flops_performed = -1, flops_performed_all = 0;
