@@ -463,3 +463,26 @@ def test_sharded_solve_reproduces_single_gpu_bits():
     for x, sel, it in zip(shards, sels, its):
         if it == it1:
             assert np.array_equal(x, X1[sel])
+
+
+@pytest.mark.parametrize("lmln", [(16, 16), (16, 64), (32, 32), (64, 64)], ids=lambda v: f"{v[0]}x{v[1]}")
+def test_fp64_product_runs_on_dmma_and_matches_oracle(lmln, monkeypatch):
+    """Complex fp64 with LM, LN in {16,32,64} uses the DMMA kernel (spmm_dmma.cu); same fp64 bar as the SIMT kernel
+    (<= 1e-12 * sum|terms|), and TFQMRGPU_TENSOR=0 falls back to the SIMT kernel with the same result within that bar."""
+    lm, ln = lmln
+    prob = P.random_system(12, lm, ln, seed=lm*100 + ln + 1, unsorted=True)
+    res = {}
+    for env in ("1", "0"):
+        monkeypatch.setenv("TFQMRGPU_TENSOR", env)
+        h, pl = _open(prob)
+        pl.buffer_size_for(lm, ln, "z"); pl.set_buffer()
+        assert pl.plan_info()["use_dmma"] == int(env)
+        A = O.fill_cos_sin(prob.A.nnzb, lm, lm, np.float64); X = O.fill_cos_sin(prob.X.nnzb, lm, ln, np.float64)
+        pl.set_matrix("A", A, "t", L.LAYOUT_RRRRIIII); pl.set_matrix("X", X, "n", L.LAYOUT_RRRRIIII)
+        pl.multiply(1)
+        res[env] = pl.get_vector("Y", "n", L.LAYOUT_RRRRIIII).reshape(prob.X.nnzb, 2, lm, ln)
+        lists = pl.plan_lists()
+        pl.close(); h.close()
+    Yo = O.multiply(A, X, lists["starts"], lists["pairs"], lm, ln)
+    bar = 1e-12*prob.mb*lm*2
+    assert np.abs(res["1"] - Yo).max() <= bar and np.abs(res["0"] - Yo).max() <= bar

@@ -382,6 +382,8 @@ tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, ch
         char const *env = std::getenv("TFQMRGPU_TENSOR");
         p.use_tc = spmm_tc_supported(LM, LN, precision) && !(env && '0' == env[0]);
         if (p.use_tc) g = spmm_tc_columns_per_unit(LN);   // 128 MMA rows = g * 2 * LN
+        p.use_dmma = spmm_dmma_supported(LM, LN, precision) && !(env && '0' == env[0]);
+        if (p.use_dmma) g = std::min(spmm_dmma_columns_per_unit(LM, LN), std::max(1, p.maxColsPerRow));
         p.gmax = uint32_t(g);
         std::vector<uint32_t> first, ng;
         for (int r = 0; r < p.mb; ++r) {

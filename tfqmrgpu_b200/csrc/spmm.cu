@@ -256,6 +256,7 @@ tfqmrgpuStatus_t launch_sized(Plan const &p, void *y, void const *x, int expect,
 tfqmrgpuStatus_t launch_spmm(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream)
 {
     if (p.use_tc) return launch_spmm_tc(p, y, x, expect, stream);
+    if (p.use_dmma) return launch_spmm_dmma(p, y, x, expect, stream);
     switch (p.LM*1000 + p.LN) {
 #define TFQ_CASE(LM, LN) case LM*1000 + LN: return launch_sized<LM, LN>(p, y, x, expect, stream);
         TFQ_CASE( 4,  4) TFQ_CASE( 4,  5) TFQ_CASE( 4,  8) TFQ_CASE( 4, 32)

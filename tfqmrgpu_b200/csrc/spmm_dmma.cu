@@ -7,8 +7,10 @@
 // peak (measured 22.8 TFLOP/s at 32x32), a warp tile of 2 x 4 DMMA tiles needs 96 bytes per 256.
 //
 // One CTA per unit (a block row times G block columns, G*LN = 64 ... 256).  Per pipeline step one k-slab (KC rows) of
-// the A block and of the unit's X blocks is staged by the bulk-copy engine, ONE ROW PER COPY into rows padded by 8
-// doubles, which makes the 64-bit fragment loads (4 k-rows x 8 columns per warp) conflict-free.
+// the A block and of the unit's X blocks is staged by the bulk-copy engine, one copy per (operand, Re|Im) plane.
+// The 64-bit fragment loads (4 k-rows x 8 columns per warp) are 4-way bank-conflicted in this unpadded layout; a
+// padded layout needs one bulk copy per ROW, which was measured to be copy-engine bound and slower (47.5 ms vs
+// 31.0 ms per product at 32x32, 128 RHS; the SIMT kernel: 40.6 ms).  A swizzled 2-D TMA box is the next step.
 // Complex arithmetic: Yr += Ar*Xr + (-Ai)*Xi ; Yi += Ar*Xi + Ai*Xr  -> 4 DMMAs per (8x8 tile, 4 k).
 // Fragments (PTX ISA, m8n8k4 .row.col): a = Amma[lane/4][lane%4], b = Bmma[lane%4][lane/4],
 // c0,c1 = C[lane/4][2*(lane%4) + {0,1}] with Amma[i][k] = A[k][i] (A is stored transposed) and Bmma[k][j] = X[k][j].
@@ -20,7 +22,6 @@ namespace tfq {
 namespace {
 
 constexpr int kKC = 8;          // k rows per pipeline step
-constexpr int kPad = 8;         // doubles of padding per staged row
 constexpr int kMaxStagesD = 4;
 
 struct DmmaArgs {
@@ -65,7 +66,7 @@ spmm_dmma_kernel(DmmaArgs const a)
     static_assert(LM % 16 == 0 && LN % 16 == 0, "warp tile = 16 rows x 32 columns");
     constexpr int WR = LM/16;                       // warps along the rows
     constexpr int CH = LM/kKC;                      // pipeline steps per entry
-    constexpr int SA = LM + kPad, SX = LN + kPad;   // padded row strides (doubles)
+    constexpr int SA = LM, SX = LN;                 // row strides of the staged slabs (doubles)
 
     if (a.expect >= 0 && a.ctl->state != a.expect) return; // device-resident solver control
 
@@ -102,7 +103,7 @@ spmm_dmma_kernel(DmmaArgs const a)
     __syncthreads();
     int const ng = s_ng;
 
-    // producer: warp 0, one bulk copy per staged row
+    // producer: warp 0
     auto issue = [&](int st) {
         int const s = st % nStages;
         int const e = st / CH, ch = st - e*CH;
@@ -110,18 +111,16 @@ spmm_dmma_kernel(DmmaArgs const a)
         uint32_t const ia = (e < kEntCache) ? s_ent_a[e] : a.ent_a[e0 + e];
         if (0 == lane) mbar_expect_tx_d(&bars[s], unsigned((2*kKC*LM + ng*2*kKC*LN)*sizeof(double)));
         __syncwarp();
-        int const nRows = 2*kKC + ng*2*kKC;
-        for (int r = lane; r < nRows; r += 32) {
-            if (r < 2*kKC) {
-                int const c = r / kKC, kk = r % kKC;
-                double const *src = a.A + (size_t(ia)*2 + c)*LM*LM + size_t(ch*kKC + kk)*LM;
-                bulk_g2s_d(dst + r*SA, src, unsigned(LM*sizeof(double)), &bars[s]);
+        for (int c = lane; c < 2 + 2*ng; c += 32) {   // contiguous slabs: one copy per (operand, Re|Im) plane
+            if (c < 2) {
+                double const *src = a.A + (size_t(ia)*2 + c)*LM*LM + size_t(ch)*kKC*LM;
+                bulk_g2s_d(dst + c*kKC*SA, src, unsigned(kKC*LM*sizeof(double)), &bars[s]);
             } else {
-                int const q = r - 2*kKC, gg = q/(2*kKC), c = (q/kKC) & 1, kk = q % kKC;
+                int const gg = (c - 2) >> 1, ri = (c - 2) & 1;
                 uint32_t const ix = (e < kEntCache) ? s_ent_x[e*G + gg] : a.ent_x[size_t(e0 + e)*G + gg];
                 double const *base = (kNoBlock == ix) ? a.zero : a.x + size_t(ix)*2*LM*LN;
-                double const *src = base + size_t(c)*LM*LN + size_t(ch*kKC + kk)*LN;
-                bulk_g2s_d(dst + 2*kKC*SA + q*SX, src, unsigned(LN*sizeof(double)), &bars[s]);
+                double const *src = base + size_t(ri)*LM*LN + size_t(ch)*kKC*LN;
+                bulk_g2s_d(dst + 2*kKC*SA + (gg*2 + ri)*kKC*SX, src, unsigned(kKC*LN*sizeof(double)), &bars[s]);
             }
         }
     };
@@ -199,7 +198,7 @@ template <int LM, int LN>
 tfqmrgpuStatus_t launch_d(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream)
 {
     int const G = int(p.gmax);
-    size_t const stageBytes = (2*size_t(kKC)*(LM + kPad) + size_t(G)*2*kKC*(LN + kPad))*sizeof(double);
+    size_t const stageBytes = (2*size_t(kKC)*LM + size_t(G)*2*kKC*LN)*sizeof(double);
     int const stages = int(std::min<size_t>(kMaxStagesD, std::max<size_t>(2, (96*1024)/stageBytes)));
     size_t const smem = 128 + stages*stageBytes;
     int const warps = (LM/16)*((G*LN + 31)/32);

@@ -76,6 +76,7 @@ struct Plan {
     // block-size dependent: SpMM units (one CTA each): a block row times <= gmax block columns
     uint32_t nUnits = 0, gmax = 1; uint64_t nEntries = 0;
     bool use_tc = false;              // block-sparse product on the tensor cores (spmm_tc.cu)
+    bool use_dmma = false;            // complex fp64 product on the FP64 tensor pipe (spmm_dmma.cu)
     uint32_t *d_unit_e0 = nullptr;    // [nUnits+1] first entry of every unit
     uint32_t *d_unit_y = nullptr;     // [nUnits*gmax] storage index of the unit's Y blocks (kNoBlock = none)
     uint32_t *d_ent_a = nullptr;      // [nEntries] A block of the entry
@@ -127,6 +128,10 @@ tfqmrgpuStatus_t launch_spmm(Plan const &p, void *y, void const *x, int expect, 
 bool spmm_tc_supported(int LM, int LN, char precision);
 int  spmm_tc_columns_per_unit(int LN);
 tfqmrgpuStatus_t launch_spmm_tc(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream);
+// DMMA variant (spmm_dmma.cu): complex fp64, LM and LN in {16, 32, 64}; also switched off by TFQMRGPU_TENSOR=0
+bool spmm_dmma_supported(int LM, int LN, char precision);
+int  spmm_dmma_columns_per_unit(int LM, int LN);
+tfqmrgpuStatus_t launch_spmm_dmma(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream);
 // fused vector algebra, see vecops.cu
 enum VecOp : int { OP_INIT = 0, OP_K1, OP_E1, OP_K2, OP_K3, OP_E2, OP_K4, OP_N3, OP_COUNT };
 tfqmrgpuStatus_t launch_vecop(Plan const &p, int op, cudaStream_t stream);
