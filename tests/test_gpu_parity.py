@@ -486,3 +486,47 @@ def test_fp64_product_runs_on_dmma_and_matches_oracle(lmln, monkeypatch):
     Yo = O.multiply(A, X, lists["starts"], lists["pairs"], lm, ln)
     bar = 1e-12*prob.mb*lm*2
     assert np.abs(res["1"] - Yo).max() <= bar and np.abs(res["0"] - Yo).max() <= bar
+
+
+def test_fortran_shims_full_solve():
+    """The 18 by-reference `name_` shims (tfqmrgpu_Fortran_wrappers.c:58-187) drive a complete solve of the Julia
+    known-answer test with 1-based index arrays, like the reference's Fortran module does
+    (tfqmrgpu_Fortran_module.F90:336-421)."""
+    import ctypes as C
+    lib = L.load()
+    k = P.julia_kat()
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    rpA, ciA, rpX, ciX, rpB, ciB = [i32(v + 1) for v in (k.A.rowptr, k.A.colind, k.X.rowptr, k.X.colind, k.B.rowptr, k.B.colind)]
+    vA = P.interleave(k.A.val, np.float64); vB = P.interleave(k.B.val, np.float64)
+    ip = lambda a: a.ctypes.data_as(C.c_void_p)
+    ref = lambda v: C.byref(v)
+    stat = C.c_int32(-1)
+    h, plan, buf = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    lib.tfqmrgpucreatehandle_(ref(h), ref(stat)); assert stat.value == 0
+    stream = C.c_int64(0)
+    lib.tfqmrgpusetstream_(ref(h), ref(stream), ref(stat)); assert stat.value == 0
+    mb, nA, nX, nB, echo = C.c_int32(k.mb), C.c_int32(len(ciA)), C.c_int32(len(ciX)), C.c_int32(len(ciB)), C.c_int32(0)
+    lib.tfqmrgpu_bsrsv_createplan_(ref(h), ref(plan), ref(mb), ip(rpA), ref(nA), ip(ciA), ip(rpX), ref(nX), ip(ciX),
+                                   ip(rpB), ref(nB), ip(ciB), ref(echo), ref(stat)); assert stat.value == 0
+    ldA, ldB, size, prec = C.c_int32(k.lm), C.c_int32(k.ln), C.c_size_t(0), C.c_char(b"z")
+    lib.tfqmrgpu_bsrsv_buffersize_(ref(h), ref(plan), ref(ldA), ref(ldA), ref(ldB), ref(ldB), ref(prec), ref(size), ref(stat))
+    assert stat.value == 0 and size.value > 0
+    lib.tfqmrgpucreateworkspace_(ref(buf), ref(size), ref(stat)); assert stat.value == 0
+    lib.tfqmrgpu_bsrsv_setbuffer_(ref(h), ref(plan), ref(buf), ref(stat)); assert stat.value == 0
+    layout, tr = C.c_int32(L.LAYOUT_RIRIRIRI), C.c_char(b"n")
+    for var, val, ld, d2 in ((b"A", vA, ldA, ldA), (b"B", vB, ldB, ldA)):
+        v = C.c_char(var)
+        lib.tfqmrgpu_bsrsv_setmatrix_z_(ref(h), ref(plan), ref(v), ip(val), ref(ld), ref(d2), ref(tr), ref(layout), ref(stat))
+        assert stat.value == 0
+    thr, maxit = C.c_double(1.2e-8), C.c_int32(210)
+    lib.tfqmrgpu_bsrsv_solve_(ref(h), ref(plan), ref(thr), ref(maxit), ref(stat)); assert stat.value == 0
+    res, it, fl, fla = C.c_double(), C.c_int32(), C.c_double(), C.c_double()
+    lib.tfqmrgpu_bsrsv_getinfo_(ref(h), ref(plan), ref(res), ref(it), ref(fl), ref(fla), ref(stat)); assert stat.value == 0
+    assert res.value <= 1.2e-8 and 5 <= it.value <= 9 and fl.value > 0
+    X = np.zeros((len(ciX), k.lm, k.ln, 2)); vx = C.c_char(b"X")
+    lib.tfqmrgpu_bsrsv_getmatrix_z_(ref(h), ref(plan), ref(vx), ip(X), ref(ldB), ref(ldA), ref(tr), ref(layout), ref(stat))
+    assert stat.value == 0
+    assert np.abs((X[..., 0] + 1j*X[..., 1]) - k.X_exact).max() < 1e-7
+    lib.tfqmrgpu_bsrsv_destroyplan_(ref(h), ref(plan), ref(stat)); assert stat.value == 0 and not plan.value
+    lib.tfqmrgpudestroyworkspace_(ref(buf), ref(stat)); assert stat.value == 0
+    lib.tfqmrgpudestroyhandle_(ref(h), ref(stat)); assert stat.value == 0 and not h.value
