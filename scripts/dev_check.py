@@ -1,6 +1,6 @@
 # dev-only quick GPU check (not a test): plan parity, SpMM parity, solve parity on small problems
 import sys, time, numpy as np
-sys.path.insert(0, 'tests')
+sys.path.insert(0, '.'); sys.path.insert(0, 'oracle')
 import orclib as O
 from tfqmrgpu_b200 import problems as P, api, _lib as L
 

@@ -112,9 +112,6 @@ spmm_unit_kernel(SpmmArgs<real_t> const a)
     int const nSteps = nE*CH;
 
     int const tid = threadIdx.x;
-    int const NTJ = (G*LN)/TJ;
-    int const tj = tid % NTJ, ti = tid / NTJ;
-    int const g = (tj*TJ)/LN, j0 = (tj*TJ) % LN, i0 = ti*TI;
 
     if (tid < 16) s_y[tid] = (tid < G) ? a.unit_y[size_t(u)*G + tid] : kNoBlock;
     {
@@ -130,6 +127,10 @@ spmm_unit_kernel(SpmmArgs<real_t> const a)
     if (0 == tid) { int n = 0; for (int q = 0; q < G; ++q) n += (s_y[q] != kNoBlock); s_ng = n; }
     __syncthreads();
     int const ng = s_ng;
+    // thread tile mapping over the ng block columns this unit really has (ragged rows: whole warps idle, not lanes)
+    int const NTJ = (ng*LN)/TJ;
+    int const tj = (NTJ > 0) ? tid % NTJ : 0, ti = (NTJ > 0) ? tid / NTJ : LM;
+    int const g = (tj*TJ)/LN, j0 = (tj*TJ) % LN, i0 = ti*TI;
     bool const active = (ti < LM/TI) && (g < ng);
 
     // producer: warp 0 issues the bulk copies of one pipeline step
@@ -141,6 +142,21 @@ spmm_unit_kernel(SpmmArgs<real_t> const a)
         int const lane = tid;
         if (0 == lane) mbar_expect_tx(&bars[s], unsigned(2*KC*(LM + ng*LN)*sizeof(real_t)));
         __syncwarp();
+        if (KC == LM) {
+            // the whole block per step: its Re and Im planes are contiguous in memory AND in the stage, so ONE copy per
+            // operand (the copy engine retires small copies at a fixed ~50 cycles each; this halves their number)
+            for (int c = lane; c < 1 + ng; c += 32) {
+                if (0 == c) {
+                    bulk_g2s(dst, a.A + size_t(ia)*2*LM*LM, unsigned(2*LM*LM*sizeof(real_t)), &bars[s]);
+                } else {
+                    int const gg = c - 1;
+                    uint32_t const ix = (e < kEntCache) ? s_ent_x[e*G + gg] : a.ent_x[size_t(e0 + e)*G + gg];
+                    real_t const *src = (kNoBlock == ix) ? a.zero : a.x + size_t(ix)*2*LM*LN;   // (the zero block is a full block)
+                    bulk_g2s(dst + 2*KC*LM + gg*2*KC*LN, src, unsigned(2*LM*LN*sizeof(real_t)), &bars[s]);
+                }
+            }
+            return;
+        }
         for (int c = lane; c < 2 + 2*ng; c += 32) {
             if (c < 2) {
                 real_t const *src = a.A + (size_t(ia)*2 + c)*LM*LM + size_t(ch)*KC*LM;
