@@ -186,19 +186,31 @@ def run_ours(args):
     es = 8 if prec == "z" else 4
 
     # this rank's shard: block columns [rank*ncols, (rank+1)*ncols) of a world*ncols-column problem, A replicated
-    sp = synthetic.Stencil27(n, lm, ln, ncols, sigma=args.sigma, dtype=dt, device=dev, col0=rank*ncols, ncols_global=world*ncols)
+    sp = synthetic.Stencil27(n, lm, ln, ncols, sigma=args.sigma, dtype=dt, device=dev, col0=rank*ncols, ncols_global=world*ncols,
+                             with_values=(0 == rank))
     h = api.Handle(torch.cuda.current_stream(dev).cuda_stream)
     pl = api.BsrsvPlan(h, sp.mb, sp.rpA, sp.ciA, sp.rpX, sp.ciX, sp.rpB, sp.ciB)
     nbytes = pl.buffer_size_for(lm, ln, prec)
-    pl.set_buffer()
+    # caller-owned workspace as a torch tensor, so that the A window can be the target of an NCCL broadcast
+    ws_t = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+    ws_ptr = (ws_t.data_ptr() + 255) & ~255
+    pl.set_buffer(ws_ptr, keep_alive=ws_t)
+    a_off, a_len = pl.window("A")
+    a_win = ws_t[(ws_ptr - ws_t.data_ptr()) + a_off:(ws_ptr - ws_t.data_ptr()) + a_off + a_len]
     info = pl.plan_info()
-    a_ptr = sp.valA_host.data_ptr()
+    a_ptr = sp.valA_host.data_ptr() if 0 == rank else 0
     valB = torch.from_numpy(sp.valB).pin_memory()
     x_host = torch.empty(sp.nnzbX*lm*ln*2, dtype=torch.float64 if prec == "z" else torch.float32).pin_memory()
     x_np = x_host.numpy()
 
     def upload():
-        pl.set_matrix("A", None, "n", raw_ptr=a_ptr)
+        # A is replicated: rank 0 uploads it over PCIe (setMatrix: H2D + layout conversion) and the converted operand goes
+        # to the other ranks' A windows over NVLink (the only collective of the path; it replaces N-1 PCIe uploads of 7 GB
+        # that would contend for the host's memory bandwidth).  B and X are per rank.
+        if world == 1 or rank == 0:
+            pl.set_matrix("A", None, "n", raw_ptr=a_ptr)
+        if world > 1:
+            dist.broadcast(a_win, src=0)
         pl.set_matrix("B", None, "n", raw_ptr=valB.data_ptr())
 
     def barrier():
@@ -246,7 +258,7 @@ def run_ours(args):
     last = pl.info()
 
     # ---- end to end through the C-ABI with host buffers -------------------------------------------------------
-    h2d = sp.a_bytes + valB.numel()*valB.element_size()
+    h2d = sp.a_bytes + valB.numel()*valB.element_size()          # rank 0 (the other ranks upload B only when N > 1)
     d2h = x_host.numel()*x_host.element_size()
     e2e_flops = 0
     barrier()
@@ -296,6 +308,7 @@ def run_ours(args):
                        "residual_reached": last["residuum"], "status": int(statuses[-1]), "worst_status_over_ranks": worst_status,
                        "workspace_bytes": nbytes, "nnzbA": sp.nnzbA, "nnzbX": nnzbX, "nPairs": nPairs},
             "e2e": {"value": e2e_total/e2e_s*1e-9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "a_distribution": "rank 0 H2D + NCCL broadcast over NVLink" if world > 1 else "H2D",
                     "ms_per_step": 1e3*e2e_s/args.steps},
             "gpu_launches": int(launches),
             "roofline": roofline,

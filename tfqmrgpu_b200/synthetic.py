@@ -39,7 +39,7 @@ class Stencil27:
     [nnzbA, lm, lm, 2] in the caller's RIRIRIRI layout; all index arrays are numpy int32."""
 
     def __init__(self, n, lm, ln, ncols, sigma=8.0, seed=1234, dtype=np.float32, device="cuda", pin=True,
-                 chunk_blocks=1 << 15, col0=0, ncols_global=None):
+                 chunk_blocks=1 << 15, col0=0, ncols_global=None, with_values=True):
         import torch
         self.n, self.lm, self.ln, self.ncols, self.sigma, self.seed = n, lm, ln, ncols, sigma, seed
         self.mb = n**3
@@ -61,6 +61,10 @@ class Stencil27:
             valB[:, j % lm, j, 0] = 1
         self.valB = valB
         tdt = torch.float64 if dtype == np.float64 else torch.float32
+        self._a_bytes = self.nnzbA*lm*lm*2*(8 if dtype == np.float64 else 4)
+        self.valA_host = None
+        if not with_values:      # a rank that receives the replicated operator from a peer needs the index arrays only
+            return
         self.valA_host = torch.empty((self.nnzbA, lm, lm, 2), dtype=tdt, pin_memory=pin)
         dev = torch.device(device)
         per = lm*lm*2
@@ -81,4 +85,4 @@ class Stencil27:
 
     @property
     def a_bytes(self):
-        return self.valA_host.numel()*self.valA_host.element_size()
+        return self._a_bytes
