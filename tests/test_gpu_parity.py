@@ -530,3 +530,26 @@ def test_fortran_shims_full_solve():
     lib.tfqmrgpu_bsrsv_destroyplan_(ref(h), ref(plan), ref(stat)); assert stat.value == 0 and not plan.value
     lib.tfqmrgpudestroyworkspace_(ref(buf), ref(stat)); assert stat.value == 0
     lib.tfqmrgpudestroyhandle_(ref(h), ref(stat)); assert stat.value == 0 and not h.value
+
+
+@pytest.mark.parametrize("lmln,level,expect", [((16, 16), "1", 1), ((16, 64), "1", 1), ((64, 64), "1", 0), ((64, 64), "2", 1)],
+                         ids=["16x16", "16x64", "64x64-default-simt", "64x64-optin"])
+def test_tensor_core_product_other_block_sizes(lmln, level, expect, monkeypatch):
+    """tcgen05 path for LM = 16 (default) and LM = 64 (opt-in with TFQMRGPU_TENSOR=2, see spmm_tc.cu): product within
+    1e-4 absolute of the fp32 oracle (bench_tfqmrgpu.cu:414) and within 2e-6 * sum|terms| of an fp64 evaluation."""
+    lm, ln = lmln
+    monkeypatch.setenv("TFQMRGPU_TENSOR", level)
+    prob = P.random_system(12, lm, ln, seed=lm*100 + ln + 2, unsorted=True)
+    h, pl = _open(prob)
+    pl.buffer_size_for(lm, ln, "c"); pl.set_buffer()
+    assert pl.plan_info()["use_tc"] == expect
+    A = O.fill_cos_sin(prob.A.nnzb, lm, lm, np.float32); X = O.fill_cos_sin(prob.X.nnzb, lm, ln, np.float32)
+    pl.set_matrix("A", A, "t", L.LAYOUT_RRRRIIII); pl.set_matrix("X", X, "n", L.LAYOUT_RRRRIIII)
+    pl.multiply(1)
+    Y = pl.get_vector("Y", "n", L.LAYOUT_RRRRIIII).reshape(prob.X.nnzb, 2, lm, ln)
+    lists = pl.plan_lists()
+    pl.close(); h.close()
+    Y32 = O.multiply(A, X, lists["starts"], lists["pairs"], lm, ln)
+    Y64 = O.multiply(A.astype(np.float64), X.astype(np.float64), lists["starts"], lists["pairs"], lm, ln)
+    assert np.abs(Y - Y32).max() <= 1e-4
+    assert np.abs(Y - Y64).max() <= 2e-6*prob.mb*lm*4

@@ -380,9 +380,10 @@ tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, ch
         // keep one pipeline stage (A block + g X blocks, possibly k-chunked) reasonable: <= 48 KiB at 4 k-rows
         while (g > 1 && 2*4*(size_t(LM) + size_t(g)*LN)*s > 48*1024) --g;
         char const *env = std::getenv("TFQMRGPU_TENSOR");
-        p.use_tc = spmm_tc_supported(LM, LN, precision) && !(env && '0' == env[0]);
+        int const level = env ? std::atoi(env) : 1;
+        p.use_tc = spmm_tc_supported(LM, LN, precision, level);
         if (p.use_tc) g = spmm_tc_columns_per_unit(LN);   // 128 MMA rows = g * 2 * LN
-        p.use_dmma = spmm_dmma_supported(LM, LN, precision) && !(env && '0' == env[0]);
+        p.use_dmma = spmm_dmma_supported(LM, LN, precision) && (level >= 1);
         if (p.use_dmma) g = std::min(spmm_dmma_columns_per_unit(LM, LN), std::max(1, p.maxColsPerRow));
         p.gmax = uint32_t(g);
         std::vector<uint32_t> first, ng;

@@ -36,8 +36,8 @@ namespace {
 
 constexpr int kConvWarps = 8, kConvThreads = 32*kConvWarps;   // converter warps; warp 8 issues copies and MMAs
 constexpr int kTcThreads = kConvThreads + 32;
-constexpr uint32_t kTmemCols = 256;     // [0,64): accumulator, [64,128): correction accumulator, [128,256): two X operand stages
-constexpr uint32_t kTmemStage0 = 128;
+// Tensor memory per CTA: [0, 2N): accumulator (main sum | correction sum), then two X operand stages of 2*LM columns (hi | lo).
+// LM = 16: 64 + 2*32 = 128 columns, LM = 32: 128 + 2*64 = 256 (two CTAs per SM), LM = 64: 256 + 2*128 = 512 (one CTA per SM)
 
 struct TcArgs {
     float *y; float const *x; float const *A;
@@ -104,12 +104,23 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, uint32_t const (&r)[16]) {
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, uint32_t const *r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, uint32_t const *r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
                  :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
                     "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                  "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -144,14 +155,23 @@ __device__ __forceinline__ uint64_t smem_desc_noswizzle(uint32_t saddr, uint32_t
     return d;                                        // base offset 0, layout type 0 = no swizzle
 }
 
-constexpr int kRingA = 6;                            // raw A blocks in flight per CTA (bulk-copy ring)
+
+template <int LM> struct TcShape {
+    static constexpr int ring = (64 == LM) ? 3 : 6;                    // A blocks in flight per CTA (bulk-copy ring)
+    static constexpr int ctas = (64 == LM) ? 1 : 2;                    // resident CTAs per SM (TMEM columns)
+    static constexpr uint32_t acc_cols = 4*LM, stage_cols = 2*LM;      // accumulator (2N), one X stage (hi | lo)
+    static constexpr uint32_t tmem_cols = (acc_cols + 2*stage_cols <= 128) ? 128 : ((acc_cols + 2*stage_cols <= 256) ? 256 : 512);
+};
 
 template <int LM, int LN>
-__global__ void __launch_bounds__(kTcThreads, 2)
+__global__ void __launch_bounds__(kTcThreads, TcShape<LM>::ctas)
 spmm_tc_kernel(TcArgs const a)
 {
-    static_assert(LM == 32, "k range per thread is LM/2 = 16 (tcgen05.st .x16)");
-    static_assert(LN == 32 || LN == 64, "128 MMA rows = G * 2 * LN");
+    static_assert(LM == 16 || LM == 32 || LM == 64, "k range per thread is LM/2 (tcgen05.st .x8 / .x16)");
+    static_assert(LN == 16 || LN == 32 || LN == 64, "128 MMA rows = G * 2 * LN");
+    constexpr int kRingA = TcShape<LM>::ring;
+    constexpr uint32_t kTmemCols = TcShape<LM>::tmem_cols, kTmemStage0 = TcShape<LM>::acc_cols, kStageCols = TcShape<LM>::stage_cols;
+    constexpr int KH = LM/2;              // k values per converter thread (two warps share a lane quarter)
     constexpr int G  = 64/LN;             // block columns per unit
     constexpr int N  = 2*LM;              // MMA N: (Re|Im of A, i)
     constexpr int KS = LM/8;              // k-steps of 8 (TF32) per entry
@@ -236,7 +256,7 @@ spmm_tc_kernel(TcArgs const a)
             tc_fence_after();
             if (leader) {
                 uint32_t const sa = ring_u32 + uint32_t(r)*SLOT;
-                uint32_t const xa = tmem_base + kTmemStage0 + uint32_t(s)*64;
+                uint32_t const xa = tmem_base + kTmemStage0 + uint32_t(s)*kStageCols;
                 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
                     uint64_t const b = smem_desc_noswizzle(sa + ks*KSB, LBO, SBO);
@@ -244,7 +264,7 @@ spmm_tc_kernel(TcArgs const a)
                     // main sum in columns [0,N), correction sum in [N,2N): the tensor core truncates the fp32 accumulator
                     // once per MMA, so the small correction products must not share the large sum's accumulator
                     mma_tf32_ts(tmem_base,     xa + 8*ks,      b, IDESC_2N, first);   // Xhi * [Ahi ; Alo]
-                    mma_tf32_ts(tmem_base + N, xa + 32 + 8*ks, b, IDESC_N,  1u);      // Xlo * Ahi
+                    mma_tf32_ts(tmem_base + N, xa + LM + 8*ks, b, IDESC_N,  1u);      // Xlo * Ahi
                 }
                 mma_commit(&bar_mma[s]);
             }
@@ -257,40 +277,45 @@ spmm_tc_kernel(TcArgs const a)
         int const g = m/(2*LN), cx = (m/LN) & 1, j = m % LN;
         uint32_t const iy = s_y[g];
         bool const has_g = (g < gs) && (kNoBlock != iy);
-        uint32_t const xoff = uint32_t(cx)*LM*LN + uint32_t(16*h)*LN + uint32_t(j);
+        uint32_t const xoff = uint32_t(cx)*LM*LN + uint32_t(KH*h)*LN + uint32_t(j);
         auto x_index = [&](int e) -> uint32_t { return (has_g && e < nE) ? a.ent_x[size_t(e0 + e)*gs + g] : kNoBlock; };
-        auto load_x = [&](uint32_t ix, float (&xr)[16]) {
+        auto load_x = [&](uint32_t ix, float (&xr)[KH]) {
             if (kNoBlock != ix) {
                 float const *xp = a.x + size_t(ix)*XBLK + xoff;
                 #pragma unroll
-                for (int r = 0; r < 16; ++r) xr[r] = __ldg(xp + r*LN);
+                for (int r = 0; r < KH; ++r) xr[r] = __ldg(xp + r*LN);
             } else {
                 #pragma unroll
-                for (int r = 0; r < 16; ++r) xr[r] = 0.f;
+                for (int r = 0; r < KH; ++r) xr[r] = 0.f;
             }
         };
         // one entry: xc holds its X values; the loads of entry e+1 go to xn while entry e is split
-        auto step = [&](int e, float (&xc)[16], float (&xn)[16], uint32_t ix_next, uint32_t &ix_next2) {
+        auto step = [&](int e, float (&xc)[KH], float (&xn)[KH], uint32_t ix_next, uint32_t &ix_next2) {
             int const s = e & 1, r = e % kRingA;
             load_x(ix_next, xn);
             ix_next2 = x_index(e + 2);
             if (e >= 2) { mbar_wait(&bar_mma[s], unsigned(((e >> 1) - 1) & 1)); tc_fence_after(); } // stage s is free again
             // ---- X operand: split, registers -> tensor memory (lane = m, column = k) ------------------------
             {
-                uint32_t hi[16], lo[16];
+                uint32_t const t0 = tmem_base + (uint32_t(32*q) << 16) + kTmemStage0 + uint32_t(s)*kStageCols + uint32_t(KH*h);
+                constexpr int W = (KH < 16) ? KH : 16;             // columns per tcgen05.st
                 #pragma unroll
-                for (int t = 0; t < 16; ++t) split_rn(xc[t], hi[t], lo[t]);
-                uint32_t const t0 = tmem_base + (uint32_t(32*q) << 16) + kTmemStage0 + uint32_t(s)*64 + uint32_t(16*h);
-                tmem_st16(t0, hi);
-                tmem_st16(t0 + 32, lo);
+                for (int c = 0; c < KH/W; ++c) {
+                    uint32_t hi[W], lo[W];
+                    #pragma unroll
+                    for (int t = 0; t < W; ++t) split_rn(xc[W*c + t], hi[t], lo[t]);
+                    if (8 == W) { tmem_st8(t0 + W*c, hi); tmem_st8(t0 + LM + W*c, lo); }
+                    else        { tmem_st16(t0 + W*c, hi); tmem_st16(t0 + LM + W*c, lo); }
+                }
             }
             // ---- A operand: hi = the raw block in the ring, lo = a - trunc(a) -> shared memory ------------------
             mbar_wait(&bar_a[r], unsigned((e / kRingA) & 1));
             {
                 unsigned char *const slot = ring + size_t(r)*SLOT;
                 #pragma unroll
-                for (int c2 = 0; c2 < 2; ++c2) {
+                for (int c2 = 0; c2 < (ABLK/4 + kConvThreads - 1)/kConvThreads; ++c2) {
                     int const c = tid + kConvThreads*c2;          // (k-quad, n) chunk of 4 k values
+                    if (ABLK/4 % kConvThreads != 0 && c >= ABLK/4) break;
                     int const kq = c / N, n = c % N;
                     float4 v = *reinterpret_cast<float4 const*>(slot + size_t(kq)*2*SLAB + size_t(n)*16);
                     v.x = lo_trunc(v.x); v.y = lo_trunc(v.y); v.z = lo_trunc(v.z); v.w = lo_trunc(v.w);
@@ -305,7 +330,7 @@ spmm_tc_kernel(TcArgs const a)
         };
 
         if (nE > 0) {
-            float xa_[16], xb_[16];
+            float xa_[KH], xb_[KH];
             uint32_t i1 = x_index(1), i2 = kNoBlock;
             load_x(x_index(0), xa_);
             for (int e = 0; e < nE; e += 2) {
@@ -319,29 +344,34 @@ spmm_tc_kernel(TcArgs const a)
         }
 
         // ---- epilogue: D -> registers, combine the four real products, store Y ---------------------------------
-        float *const exch = reinterpret_cast<float*>(ring);   // [G][2][LM][LN] floats, aliases the A ring (all copies and MMAs are done)
-        uint32_t d[32];
-        if (nE > 0) {
-            uint32_t d2[32];
-            tmem_ld32(tmem_base + (uint32_t(32*q) << 16) + uint32_t(h)*LM, d);       // D[m][(ca = h, i = 0..31)]
-            tmem_ld32(tmem_base + (uint32_t(32*q) << 16) + N + uint32_t(h)*LM, d2);  // correction terms
-            tmem_wait_ld();
-            #pragma unroll
-            for (int i = 0; i < 32; ++i) d[i] = __float_as_uint(__uint_as_float(d[i]) + __uint_as_float(d2[i]));
-        } else {
-            #pragma unroll
-            for (int i = 0; i < 32; ++i) d[i] = 0u;
-        }
-        if (1 == cx) {
-            #pragma unroll
-            for (int i = 0; i < LM; ++i) exch[((g*2 + h)*LM + i)*LN + j] = __uint_as_float(d[i]);
-        }
-        asm volatile("bar.sync 1, %0;" :: "n"(kConvThreads) : "memory");     // converter warps only
-        if (0 == cx && has_g) {
-            float *const yp = a.y + size_t(iy)*XBLK + size_t(h)*LM*LN + j;       // plane h: 0 = Re, 1 = Im
-            float const sgn = h ? 1.f : -1.f;                                     // Yr = XrAr - XiAi ; Yi = XrAi + XiAr
-            #pragma unroll
-            for (int i = 0; i < LM; ++i) yp[i*LN] = __uint_as_float(d[i]) + sgn*exch[((g*2 + (1 - h))*LM + i)*LN + j];
+        float *const exch = reinterpret_cast<float*>(ring);   // [G][2][EC][LN] floats, aliases the A ring (all copies and MMAs are done)
+        constexpr int EC = (LM < 32) ? LM : 32;              // accumulator columns per pass
+        #pragma unroll 1
+        for (int c = 0; c < LM/EC; ++c) {
+            uint32_t d[EC];
+            if (nE > 0) {
+                uint32_t d2[EC];
+                uint32_t const t0 = tmem_base + (uint32_t(32*q) << 16) + uint32_t(h)*LM + uint32_t(EC*c);   // D[m][(ca = h, i)]
+                if (16 == EC) { tmem_ld16(t0, d); tmem_ld16(t0 + N, d2); } else { tmem_ld32(t0, d); tmem_ld32(t0 + N, d2); }
+                tmem_wait_ld();
+                #pragma unroll
+                for (int i = 0; i < EC; ++i) d[i] = __float_as_uint(__uint_as_float(d[i]) + __uint_as_float(d2[i]));   // main + correction
+            } else {
+                #pragma unroll
+                for (int i = 0; i < EC; ++i) d[i] = 0u;
+            }
+            if (1 == cx) {
+                #pragma unroll
+                for (int i = 0; i < EC; ++i) exch[((g*2 + h)*EC + i)*LN + j] = __uint_as_float(d[i]);
+            }
+            asm volatile("bar.sync 1, %0;" :: "n"(kConvThreads) : "memory");     // converter warps only
+            if (0 == cx && has_g) {
+                float *const yp = a.y + size_t(iy)*XBLK + size_t(h)*LM*LN + size_t(EC*c)*LN + j;   // plane h: 0 = Re, 1 = Im
+                float const sgn = h ? 1.f : -1.f;                                 // Yr = XrAr - XiAi ; Yi = XrAi + XiAr
+                #pragma unroll
+                for (int i = 0; i < EC; ++i) yp[i*LN] = __uint_as_float(d[i]) + sgn*exch[((g*2 + (1 - h))*EC + i)*LN + j];
+            }
+            if (c + 1 < LM/EC) asm volatile("bar.sync 1, %0;" :: "n"(kConvThreads) : "memory");   // exch is reused
         }
     }
     tc_fence_before();
@@ -362,9 +392,11 @@ spmm_tc_kernel(TcArgs const a)
 template <int LM, int LN>
 tfqmrgpuStatus_t launch_tc(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream)
 {
-    constexpr size_t smem = 1024 + kRingA*2*size_t(2*LM*LM)*sizeof(float) + 1024; // barriers + A ring (hi and lo slabs)
-    // two CTAs per SM (two 256-column TMEM allocations): pad the request so that a third CTA can never be resident
-    constexpr size_t smem_req = (smem < 80*1024) ? 80*1024 : smem;
+    constexpr int ring = TcShape<LM>::ring, ctas = TcShape<LM>::ctas;
+    constexpr size_t smem = 1024 + ring*2*size_t(2*LM*LM)*sizeof(float) + 1024; // barriers + A ring (hi and lo slabs)
+    // `ctas` CTAs per SM by their TMEM columns: pad the request so that one more CTA can never be resident
+    constexpr size_t smem_min = (2 == ctas) ? 80*1024 : 120*1024;
+    constexpr size_t smem_req = (smem < smem_min) ? smem_min : smem;
     auto kernel = spmm_tc_kernel<LM, LN>;
     static bool configured = false;
     if (!configured) {
@@ -377,7 +409,7 @@ tfqmrgpuStatus_t launch_tc(Plan const &p, void *y, void const *x, int expect, cu
     a.ctl = ws<Control const>(p, p.off_ctl); a.expect = expect; a.gstride = int(p.gmax); a.nUnits = p.nUnits;
     static int num_sms = 0;
     if (0 == num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
-    uint32_t const grid = std::min<uint32_t>(p.nUnits, 2u*uint32_t(num_sms));   // two CTAs per SM (TMEM: 2 x 256 columns)
+    uint32_t const grid = std::min<uint32_t>(p.nUnits, uint32_t(ctas)*uint32_t(num_sms));
     if (grid > 0) kernel<<<grid, kTcThreads, smem_req, stream>>>(a);
     TFQ_CUDA(cudaGetLastError());
     return TFQMRGPU_STATUS_SUCCESS;
@@ -385,16 +417,27 @@ tfqmrgpuStatus_t launch_tc(Plan const &p, void *y, void const *x, int expect, cu
 
 } // namespace
 
-bool spmm_tc_supported(int LM, int LN, char precision) {
-    return ('c' == precision) && (32 == LM) && (32 == LN || 64 == LN);
+// level = TFQMRGPU_TENSOR (default 1): 0 never, 1 where the attainable tfQMR residual is not worse than with the fp32 SIMT
+// product (LM = 16, 32: measured 0.5x and 0.8x of the SIMT floor), 2 also LM = 64, which is 4x faster than the SIMT product
+// but whose 216-MMA accumulation chain lifts the floor 2.3-4x (1.5e-3 vs 6.5e-4 on the 12^3 stencil) - opt-in until the
+// chain is split.
+bool spmm_tc_supported(int LM, int LN, char precision, int level) {
+    if (level < 1 || 'c' != precision) return false;
+    bool const shape = (16 == LM || 32 == LM || 64 == LM) && (16 == LN || 32 == LN || 64 == LN) && (LM <= LN);
+    return shape && (LM < 64 || level >= 2);
 }
 int spmm_tc_columns_per_unit(int LN) { return 64/LN; }
 
 tfqmrgpuStatus_t launch_spmm_tc(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream)
 {
-    if (32 == p.LM && 32 == p.LN) return launch_tc<32, 32>(p, y, x, expect, stream);
-    if (32 == p.LM && 64 == p.LN) return launch_tc<32, 64>(p, y, x, expect, stream);
-    return TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED);
+    switch (p.LM*1000 + p.LN) {
+#define TFQ_CASE(LM, LN) case LM*1000 + LN: return launch_tc<LM, LN>(p, y, x, expect, stream);
+        TFQ_CASE(16, 16) TFQ_CASE(16, 32) TFQ_CASE(16, 64)
+        TFQ_CASE(32, 32) TFQ_CASE(32, 64)
+        TFQ_CASE(64, 64)
+#undef TFQ_CASE
+        default: return TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED);
+    }
 }
 
 } // namespace tfq
