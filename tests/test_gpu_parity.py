@@ -532,11 +532,11 @@ def test_fortran_shims_full_solve():
     lib.tfqmrgpudestroyhandle_(ref(h), ref(stat)); assert stat.value == 0 and not h.value
 
 
-@pytest.mark.parametrize("lmln,level,expect", [((16, 16), "1", 1), ((16, 64), "1", 1), ((64, 64), "1", 0), ((64, 64), "2", 1)],
-                         ids=["16x16", "16x64", "64x64-default-simt", "64x64-optin"])
+@pytest.mark.parametrize("lmln,level,expect", [((16, 16), "1", 1), ((16, 64), "1", 1), ((64, 64), "1", 1), ((64, 64), "0", 0)],
+                         ids=["16x16", "16x64", "64x64", "64x64-simt"])
 def test_tensor_core_product_other_block_sizes(lmln, level, expect, monkeypatch):
-    """tcgen05 path for LM = 16 (default) and LM = 64 (opt-in with TFQMRGPU_TENSOR=2, see spmm_tc.cu): product within
-    1e-4 absolute of the fp32 oracle (bench_tfqmrgpu.cu:414) and within 2e-6 * sum|terms| of an fp64 evaluation."""
+    """tcgen05 path for LM = 16 and LM = 64 (multi-pass accumulation, see spmm_tc.cu): product within 1e-4 absolute of the
+    fp32 oracle (bench_tfqmrgpu.cu:414) and within 2e-6 * sum|terms| of an fp64 evaluation."""
     lm, ln = lmln
     monkeypatch.setenv("TFQMRGPU_TENSOR", level)
     prob = P.random_system(12, lm, ln, seed=lm*100 + ln + 2, unsorted=True)

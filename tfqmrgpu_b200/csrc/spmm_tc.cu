@@ -172,6 +172,7 @@ spmm_tc_kernel(TcArgs const a)
     constexpr int kRingA = TcShape<LM>::ring;
     constexpr uint32_t kTmemCols = TcShape<LM>::tmem_cols, kTmemStage0 = TcShape<LM>::acc_cols, kStageCols = TcShape<LM>::stage_cols;
     constexpr int KH = LM/2;              // k values per converter thread (two warps share a lane quarter)
+    constexpr int kChain = (64 == LM) ? 7 : 896/LM;   // entries per accumulation pass: LM/8 MMA steps each; 112 steps per pass (56 at LM = 64)
     constexpr int G  = 64/LN;             // block columns per unit
     constexpr int N  = 2*LM;              // MMA N: (Re|Im of A, i)
     constexpr int KS = LM/8;              // k-steps of 8 (TF32) per entry
@@ -217,8 +218,17 @@ spmm_tc_kernel(TcArgs const a)
     // persistent: two resident CTAs per SM walk the units; TMEM is allocated once, the barriers are re-armed per unit
     // (a gated-off launch of this kernel then costs a handful of CTAs instead of one per unit)
     for (uint32_t u = blockIdx.x; u < a.nUnits; u += gridDim.x) {
-    uint32_t const e0 = a.unit_e0[u];
-    int const nE = int(a.unit_e0[u + 1] - e0);
+    uint32_t const e0u = a.unit_e0[u];
+    int const nEu = int(a.unit_e0[u + 1] - e0u);
+    // Accumulation chains are cut into passes of at most kChain entries: the tensor core truncates the fp32 accumulator
+    // once per MMA, and the attainable tfQMR residual was measured to follow the chain length (LM = 64: 216 MMA steps in one
+    // chain 2.3-4x the SIMT floor, 112 steps 1.3-1.7x, 56 steps 0.6-1.0x; LM = 32: 108 steps 0.8x).  A later pass adds to
+    // the Y it finds.
+    int const nPasses = (nEu + kChain - 1)/kChain, perPass = (nPasses > 0) ? (nEu + nPasses - 1)/nPasses : 0;
+    for (int pass = 0; pass < (nPasses > 0 ? nPasses : 1); ++pass) {
+    uint32_t const e0 = e0u + uint32_t(pass*perPass);
+    int const nE = (nEu - pass*perPass < perPass) ? (nEu - pass*perPass) : perPass;
+    bool const first_pass = (0 == pass);
 
     if (tid < G) s_y[tid] = (tid < gs) ? a.unit_y[size_t(u)*gs + tid] : kNoBlock;
     if (0 == tid) {
@@ -369,7 +379,10 @@ spmm_tc_kernel(TcArgs const a)
                 float *const yp = a.y + size_t(iy)*XBLK + size_t(h)*LM*LN + size_t(EC*c)*LN + j;   // plane h: 0 = Re, 1 = Im
                 float const sgn = h ? 1.f : -1.f;                                 // Yr = XrAr - XiAi ; Yi = XrAi + XiAr
                 #pragma unroll
-                for (int i = 0; i < EC; ++i) yp[i*LN] = __uint_as_float(d[i]) + sgn*exch[((g*2 + (1 - h))*EC + i)*LN + j];
+                for (int i = 0; i < EC; ++i) {
+                    float const v = __uint_as_float(d[i]) + sgn*exch[((g*2 + (1 - h))*EC + i)*LN + j];
+                    yp[i*LN] = first_pass ? v : (yp[i*LN] + v);      // (the same thread wrote this element in the previous pass)
+                }
             }
             if (c + 1 < LM/EC) asm volatile("bar.sync 1, %0;" :: "n"(kConvThreads) : "memory");   // exch is reused
         }
@@ -382,6 +395,7 @@ spmm_tc_kernel(TcArgs const a)
         #pragma unroll
         for (int r = 0; r < kRingA; ++r) mbar_inval(&bar_a[r]);
     }
+    } // passes
     } // units
     tc_fence_before();
     __syncthreads();
@@ -417,14 +431,11 @@ tfqmrgpuStatus_t launch_tc(Plan const &p, void *y, void const *x, int expect, cu
 
 } // namespace
 
-// level = TFQMRGPU_TENSOR (default 1): 0 never, 1 where the attainable tfQMR residual is not worse than with the fp32 SIMT
-// product (LM = 16, 32: measured 0.5x and 0.8x of the SIMT floor), 2 also LM = 64, which is 4x faster than the SIMT product
-// but whose 216-MMA accumulation chain lifts the floor 2.3-4x (1.5e-3 vs 6.5e-4 on the 12^3 stencil) - opt-in until the
-// chain is split.
+// level = TFQMRGPU_TENSOR (default 1): 0 never.  With the accumulation chains cut into passes (kChain) the attainable
+// tfQMR residual is not worse than with the fp32 SIMT product for LM = 16, 32 and 64 (measured).
 bool spmm_tc_supported(int LM, int LN, char precision, int level) {
     if (level < 1 || 'c' != precision) return false;
-    bool const shape = (16 == LM || 32 == LM || 64 == LM) && (16 == LN || 32 == LN || 64 == LN) && (LM <= LN);
-    return shape && (LM < 64 || level >= 2);
+    return (16 == LM || 32 == LM || 64 == LM) && (16 == LN || 32 == LN || 64 == LN) && (LM <= LN);
 }
 int spmm_tc_columns_per_unit(int LN) { return 64/LN; }
 

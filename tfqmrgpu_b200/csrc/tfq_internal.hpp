@@ -124,7 +124,7 @@ void plan_drop_graph(Plan &p);   // forget the captured iteration body
 // ---- kernels' host launchers --------------------------------------------------------------------
 // block-sparse product y = A*x on storage-ordered vectors; gate: run only if ctl->state == expect (expect < 0: always)
 tfqmrgpuStatus_t launch_spmm(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream);
-// tcgen05 3xTF32 variant (spmm_tc.cu): complex fp32, LM = 16, 32 (64 with TFQMRGPU_TENSOR=2); off with TFQMRGPU_TENSOR=0
+// tcgen05 3xTF32 variant (spmm_tc.cu): complex fp32, LM in {16, 32, 64}; off with TFQMRGPU_TENSOR=0
 bool spmm_tc_supported(int LM, int LN, char precision, int level);
 int  spmm_tc_columns_per_unit(int LN);
 tfqmrgpuStatus_t launch_spmm_tc(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream);
