@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libtfQMRgpu.so")
+LIB_PATH = os.environ.get("TFQMRGPU_LIB", os.path.join(HERE, "lib", "libtfQMRgpu.so"))   # override: A/B builds
 
 # constants of include/tfqmrgpu.h
 STATUS_SUCCESS, STATUS_MAX_ITERATIONS, STATUS_BREAKDOWN = 0, 9, 6

@@ -379,9 +379,13 @@ spmm_tc_kernel(TcArgs const a)
                 float *const yp = a.y + size_t(iy)*XBLK + size_t(h)*LM*LN + size_t(EC*c)*LN + j;   // plane h: 0 = Re, 1 = Im
                 float const sgn = h ? 1.f : -1.f;                                 // Yr = XrAr - XiAi ; Yi = XrAi + XiAr
                 #pragma unroll
-                for (int i = 0; i < EC; ++i) {
-                    float const v = __uint_as_float(d[i]) + sgn*exch[((g*2 + (1 - h))*EC + i)*LN + j];
-                    yp[i*LN] = first_pass ? v : (yp[i*LN] + v);      // (the same thread wrote this element in the previous pass)
+                for (int i = 0; i < EC; ++i) d[i] = __float_as_uint(__uint_as_float(d[i]) + sgn*exch[((g*2 + (1 - h))*EC + i)*LN + j]);
+                if (first_pass) {
+                    #pragma unroll
+                    for (int i = 0; i < EC; ++i) yp[i*LN] = __uint_as_float(d[i]);
+                } else {            // (the same thread wrote this element in the previous pass)
+                    #pragma unroll
+                    for (int i = 0; i < EC; ++i) yp[i*LN] += __uint_as_float(d[i]);
                 }
             }
             if (c + 1 < LM/EC) asm volatile("bar.sync 1, %0;" :: "n"(kConvThreads) : "memory");   // exch is reused
