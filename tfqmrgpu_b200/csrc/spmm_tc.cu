@@ -156,6 +156,20 @@ __device__ __forceinline__ uint64_t smem_desc_noswizzle(uint32_t saddr, uint32_t
 }
 
 
+// dev-only timing ablations (scripts/dev_ablate.sh builds variants; results are WRONG with any bit set):
+//   1 no lo(A) LDS/STS, 2 no split + tcgen05.st, 4 no X loads, 8 no MMAs (commit only), 16 no A bulk copies, 32 no Y stores
+#ifndef TFQ_TC_ABLATE
+#define TFQ_TC_ABLATE 0
+#endif
+
+// dev-only timeline trace of one unit of CTA 0 (scripts/dev_tc_trace.py): clock64 stamps per entry and role
+#ifdef TFQ_TC_TRACE
+__device__ long long g_tc_trace[64*24];
+#define TFQ_TRACE(e, slot) do { if (trace_on) g_tc_trace[(e)*24 + (slot)] = clock64(); } while (0)
+#else
+#define TFQ_TRACE(e, slot) do { } while (0)
+#endif
+
 template <int LM> struct TcShape {
     static constexpr int ring = (64 == LM) ? 3 : 6;                    // A blocks in flight per CTA (bulk-copy ring)
     static constexpr int ctas = (64 == LM) ? 1 : 2;                    // resident CTAs per SM (TMEM columns)
@@ -229,6 +243,10 @@ spmm_tc_kernel(TcArgs const a)
     uint32_t const e0 = e0u + uint32_t(pass*perPass);
     int const nE = (nEu - pass*perPass < perPass) ? (nEu - pass*perPass) : perPass;
     bool const first_pass = (0 == pass);
+#ifdef TFQ_TC_TRACE
+    bool const trace_on = (0 == blockIdx.x) && (u == 3*gridDim.x) && (0 == lane) && (0 == w || 7 == w || kConvWarps == w);
+    int const tslot0 = (0 == w) ? 0 : ((7 == w) ? 7 : 14);
+#endif
 
     if (tid < G) s_y[tid] = (tid < gs) ? a.unit_y[size_t(u)*gs + tid] : kNoBlock;
     if (0 == tid) {
@@ -245,30 +263,41 @@ spmm_tc_kernel(TcArgs const a)
         // The whole warp runs the loop converged and ONE elected lane issues: with elect.sync the compiler emits
         // back-to-back UTCHMMA; a lane picked by "if (0 == lane)" costs an elect/branch loop (~125 cycles) per MMA.
         uint32_t const leader = elect_one_sync();
-        auto fetch_a = [&](int e) {
+        // Entry indices are read by the whole warp, 32 entries at a time (lane l holds entry base + l): the elected lane then
+        // never waits on an index load in front of a copy (that wait was ~450 cycles per entry in the issuer's loop).
+        // (Requesting the entry's X blocks into L2 here - cp.async.bulk.prefetch.L2 - was measured: no gain, they hit L2 anyway.)
+        uint32_t ia_l = 0;
+        auto fetch_a = [&](int e) {                 // called by the converged warp
+            if (0 == (e & 31)) ia_l = (e + lane < nE) ? a.ent_a[e0 + e + lane] : 0u;
             int const r = e % kRingA;
-            uint32_t const ia = a.ent_a[e0 + e];
-            mbar_expect_tx(&bar_a[r], unsigned(ABLK*sizeof(float)));
-            unsigned char const *src = reinterpret_cast<unsigned char const*>(a.A + size_t(ia)*ABLK);
-            #pragma unroll
-            for (int kq = 0; kq < LM/4; ++kq)      // one k-quad slab each, leaving room for the lo slab behind it
-                bulk_g2s(ring + size_t(r)*SLOT + size_t(kq)*2*SLAB, src + size_t(kq)*SLAB, SLAB, &bar_a[r]);
+            uint32_t const ia = __shfl_sync(0xffffffffu, ia_l, e & 31);
+            if (leader) {
+                if (TFQ_TC_ABLATE & 16) { mbar_arrive(&bar_a[r]); return; }
+                mbar_expect_tx(&bar_a[r], unsigned(ABLK*sizeof(float)));
+                unsigned char const *src = reinterpret_cast<unsigned char const*>(a.A + size_t(ia)*ABLK);
+                #pragma unroll
+                for (int kq = 0; kq < LM/4; ++kq)      // one k-quad slab each, leaving room for the lo slab behind it
+                    bulk_g2s(ring + size_t(r)*SLOT + size_t(kq)*2*SLAB, src + size_t(kq)*SLAB, SLAB, &bar_a[r]);
+            }
         };
-        if (leader) for (int e = 0; e < kRingA && e < nE; ++e) fetch_a(e);
+        for (int e = 0; e < kRingA && e < nE; ++e) fetch_a(e);
         uint32_t const ring_u32 = smem_u32(ring);
         for (int e = 0; e < nE; ++e) {
             int const s = e & 1, r = e % kRingA;
+            TFQ_TRACE(e, 14);
             if (e >= 2 && e - 2 + kRingA < nE) {                // ring slot of entry e-2 is free once its MMAs completed
                 mbar_wait(&bar_mma[s], unsigned(((e >> 1) - 1) & 1));
-                if (leader) fetch_a(e - 2 + kRingA);
+                fetch_a(e - 2 + kRingA);
             }
+            TFQ_TRACE(e, 15);
             mbar_wait(&bar_ready[s], unsigned((e >> 1) & 1));   // X in TMEM, lo in shared memory (and the raw A landed)
             tc_fence_after();
+            TFQ_TRACE(e, 16);
             if (leader) {
                 uint32_t const sa = ring_u32 + uint32_t(r)*SLOT;
                 uint32_t const xa = tmem_base + kTmemStage0 + uint32_t(s)*kStageCols;
                 #pragma unroll
-                for (int ks = 0; ks < KS; ++ks) {
+                for (int ks = 0; ks < ((TFQ_TC_ABLATE & 8) ? 0 : KS); ++ks) {
                     uint64_t const b = smem_desc_noswizzle(sa + ks*KSB, LBO, SBO);
                     uint32_t const first = (e > 0 || ks > 0) ? 1u : 0u;
                     // main sum in columns [0,N), correction sum in [N,2N): the tensor core truncates the fp32 accumulator
@@ -279,6 +308,7 @@ spmm_tc_kernel(TcArgs const a)
                 mma_commit(&bar_mma[s]);
             }
             __syncwarp();
+            TFQ_TRACE(e, 17);
         }
     } else {
         // ================= converter warps: X -> TMEM, lo(A) -> shared memory, epilogue ==============================
@@ -290,7 +320,7 @@ spmm_tc_kernel(TcArgs const a)
         uint32_t const xoff = uint32_t(cx)*LM*LN + uint32_t(KH*h)*LN + uint32_t(j);
         auto x_index = [&](int e) -> uint32_t { return (has_g && e < nE) ? a.ent_x[size_t(e0 + e)*gs + g] : kNoBlock; };
         auto load_x = [&](uint32_t ix, float (&xr)[KH]) {
-            if (kNoBlock != ix) {
+            if (kNoBlock != ix && !(TFQ_TC_ABLATE & 4)) {
                 float const *xp = a.x + size_t(ix)*XBLK + xoff;
                 #pragma unroll
                 for (int r = 0; r < KH; ++r) xr[r] = __ldg(xp + r*LN);
@@ -302,15 +332,21 @@ spmm_tc_kernel(TcArgs const a)
         // one entry: xc holds its X values; the loads of entry e+1 go to xn while entry e is split
         auto step = [&](int e, float (&xc)[KH], float (&xn)[KH], uint32_t ix_next, uint32_t &ix_next2) {
             int const s = e & 1, r = e % kRingA;
+            TFQ_TRACE(e, tslot0 + 0);
+            // the ~100 cycles a try_wait takes on an already completed barrier overlap with the load issue
+            bool const stage_free = (e < 2) || mbar_try_wait(&bar_mma[s], unsigned(((e >> 1) - 1) & 1));
+            bool const a_landed = mbar_try_wait(&bar_a[r], unsigned((e / kRingA) & 1));
             load_x(ix_next, xn);
             ix_next2 = x_index(e + 2);
-            if (e >= 2) { mbar_wait(&bar_mma[s], unsigned(((e >> 1) - 1) & 1)); tc_fence_after(); } // stage s is free again
+            TFQ_TRACE(e, tslot0 + 1);
+            if (e >= 2) { if (!stage_free) mbar_wait(&bar_mma[s], unsigned(((e >> 1) - 1) & 1)); tc_fence_after(); } // stage s is free again
+            TFQ_TRACE(e, tslot0 + 2);
             // ---- X operand: split, registers -> tensor memory (lane = m, column = k) ------------------------
             {
                 uint32_t const t0 = tmem_base + (uint32_t(32*q) << 16) + kTmemStage0 + uint32_t(s)*kStageCols + uint32_t(KH*h);
                 constexpr int W = (KH < 16) ? KH : 16;             // columns per tcgen05.st
                 #pragma unroll
-                for (int c = 0; c < KH/W; ++c) {
+                for (int c = 0; c < ((TFQ_TC_ABLATE & 2) ? 0 : KH/W); ++c) {
                     uint32_t hi[W], lo[W];
                     #pragma unroll
                     for (int t = 0; t < W; ++t) split_rn(xc[W*c + t], hi[t], lo[t]);
@@ -319,11 +355,13 @@ spmm_tc_kernel(TcArgs const a)
                 }
             }
             // ---- A operand: hi = the raw block in the ring, lo = a - trunc(a) -> shared memory ------------------
-            mbar_wait(&bar_a[r], unsigned((e / kRingA) & 1));
+            TFQ_TRACE(e, tslot0 + 3);
+            if (!a_landed) mbar_wait(&bar_a[r], unsigned((e / kRingA) & 1));
+            TFQ_TRACE(e, tslot0 + 4);
             {
                 unsigned char *const slot = ring + size_t(r)*SLOT;
                 #pragma unroll
-                for (int c2 = 0; c2 < (ABLK/4 + kConvThreads - 1)/kConvThreads; ++c2) {
+                for (int c2 = 0; c2 < ((TFQ_TC_ABLATE & 1) ? 0 : (ABLK/4 + kConvThreads - 1)/kConvThreads); ++c2) {
                     int const c = tid + kConvThreads*c2;          // (k-quad, n) chunk of 4 k values
                     if (ABLK/4 % kConvThreads != 0 && c >= ABLK/4) break;
                     int const kq = c / N, n = c % N;
@@ -332,11 +370,13 @@ spmm_tc_kernel(TcArgs const a)
                     *reinterpret_cast<float4*>(slot + size_t(kq)*2*SLAB + SLAB + size_t(n)*16) = v;
                 }
             }
+            TFQ_TRACE(e, tslot0 + 5);
             tmem_wait_st();
             fence_proxy_async();       // generic-proxy shared-memory writes -> visible to the tensor core
             tc_fence_before();
             __syncwarp();
             if (0 == lane) mbar_arrive(&bar_ready[s]);
+            TFQ_TRACE(e, tslot0 + 6);
         };
 
         if (nE > 0) {
@@ -375,7 +415,7 @@ spmm_tc_kernel(TcArgs const a)
                 for (int i = 0; i < EC; ++i) exch[((g*2 + h)*EC + i)*LN + j] = __uint_as_float(d[i]);
             }
             asm volatile("bar.sync 1, %0;" :: "n"(kConvThreads) : "memory");     // converter warps only
-            if (0 == cx && has_g) {
+            if (0 == cx && has_g && !(TFQ_TC_ABLATE & 32)) {
                 float *const yp = a.y + size_t(iy)*XBLK + size_t(h)*LM*LN + size_t(EC*c)*LN + j;   // plane h: 0 = Re, 1 = Im
                 float const sgn = h ? 1.f : -1.f;                                 // Yr = XrAr - XiAi ; Yi = XrAi + XiAr
                 #pragma unroll
@@ -456,3 +496,9 @@ tfqmrgpuStatus_t launch_spmm_tc(Plan const &p, void *y, void const *x, int expec
 }
 
 } // namespace tfq
+
+#ifdef TFQ_TC_TRACE
+extern "C" int tfq_tc_trace_dump(long long *host, int n) {
+    return int(cudaMemcpyFromSymbol(host, tfq::g_tc_trace, size_t(n)*sizeof(long long)));
+}
+#endif
