@@ -3,6 +3,9 @@
 #   cpu : reference CPU path (-DHAS_NO_CUDA, the reference's own fallback; SURVEY.md §8c recipe)
 #   gen : the reference's FD example generator (example/tfqmrgpu_generate_FD_example.cxx)
 #   gpu : reference CUDA kernels compiled for sm_100 (same-box GPU baseline; optional)
+#   benchcpu : the reference's bench harness on the reference CPU path (bench_tfqmrgpu.cu -DHAS_NO_CUDA + libtfqmr_ref_cpu.so)
+#             -> _ref/bench_tfqmrgpu_cpu, plus _ref/libalign256.so (LD_PRELOAD: 256-byte aligned malloc, which the CPU path's
+#             workspace allocator silently assumes); used to check that the reference's own readers accept files we write
 #   callers : the reference's OWN callers, unmodified, linked against OUR libtfQMRgpu.so (drop-in evidence):
 #             example/tfqmrgpu_C_example.c -> _ref/c_example_ours ; source/bench_tfqmrgpu.cu -> _ref/bench_tfqmrgpu_ours
 #             (and bench_tfqmrgpu_ref linked against _ref/libtfqmr_ref_gpu.so for same-box comparisons)
@@ -34,6 +37,16 @@ if [ "$what" = all ] || [ "$what" = gpu ]; then
         -include cstdint $INC -shared "$REF/tfQMRgpu/source/tfqmrgpu.cu" "$HERE/ref_harness.cpp" \
         -o "$OUT/libtfqmr_ref_gpu.so" -lcurand
     echo "built $OUT/libtfqmr_ref_gpu.so"
+  fi
+fi
+if [ "$what" = all ] || [ "$what" = benchcpu ]; then
+  if [ -f "$OUT/libtfqmr_ref_cpu.so" ]; then
+    g++ -std=c++14 $SAFE -fopenmp -DHAS_NO_CUDA -include "$HERE/ref_shim.h" $INC \
+        -x c++ "$REF/tfQMRgpu/source/bench_tfqmrgpu.cu" -o "$OUT/bench_tfqmrgpu_cpu" \
+        -L"$OUT" -ltfqmr_ref_cpu -Wl,-rpath,'$ORIGIN'
+    printf '#include <stdlib.h>\nvoid *malloc(size_t n) { void *p = 0; return posix_memalign(&p, 256, n ? n : 1) ? 0 : p; }\n' \
+      | gcc -O2 -fPIC -shared -x c - -o "$OUT/libalign256.so"
+    echo "built $OUT/bench_tfqmrgpu_cpu"
   fi
 fi
 if [ "$what" = all ] || [ "$what" = callers ]; then

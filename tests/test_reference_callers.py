@@ -52,6 +52,26 @@ def test_reference_bench_harness_same_output_with_both_libraries():
     assert abs(vals["ours"][1] - vals["ref"][1]) <= 1e-8*vals["ref"][1]
 
 
+@pytest.mark.skipif(not _have("bench_tfqmrgpu_ours"), reason="reference bench not built")
+def test_reference_bench_reads_files_we_wrote(tmp_path):
+    """SURVEY 8f item 2 end to end on the GPU: the reference's harness (its XML reader and its legacy text reader) + our library
+    solve the original FD_problem.xml, our re-written XML (no indirection, scale folded in) and our legacy dump alike."""
+    from tfqmrgpu_b200 import formats as F
+    gold = os.path.join(ROOT, "tests", "golden", "FD_problem.xml")
+    prob = P.read_xml(gold)
+    ours_xml, ours_txt = str(tmp_path / "ours.xml"), str(tmp_path / "ours_problem.txt")
+    F.write_xml(ours_xml, F.xml_from_problem(prob), lossless=True)
+    F.write_legacy(ours_txt, prob)
+    vals = []
+    for f in (gold, ours_xml, ours_txt):
+        out = subprocess.run([os.path.join(REFDIR, "bench_tfqmrgpu_ours"), "tfQMR", f, "z"], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        m = re.search(r"# GPU maxdev ([0-9.e+-]+) avgdev ([0-9.e+-]+)", out.stdout)
+        assert m, out.stdout[-2000:]
+        vals.append((float(m.group(1)), float(m.group(2))))
+    assert vals[1] == vals[0] and vals[2] == vals[0]
+
+
 CASES = golden_cases()
 
 

@@ -14,7 +14,6 @@ Sources mirrored (file:line relative to the reference checkout):
 from __future__ import annotations
 
 import dataclasses
-import xml.etree.ElementTree as ET
 
 import numpy as np
 
@@ -245,43 +244,10 @@ def read_xml(path: str) -> Problem:
     """LinearProblem XML reader (tfqmrgpu_example_xml_reader.hxx:105-295): NonzerosPerRow | RowStart,
     ColumnIndex, optional Indirection, DataTensor real|complex with ``scale``.  Blocks in the file are
     Fortran/column-major per block, which is why the reference bench uploads with trans 't'
-    (bench_tfqmrgpu.cu:153-157); here blocks are returned as stored, ``val[nnzb, dim1, dim2]``."""
-    root = ET.parse(path).getroot()
-    assert root.tag == "LinearProblem"
-    tol = float(root.attrib.get("tolerance", "0"))
-    ops: dict[str, Bsr] = {}
-    dims: dict[str, tuple[int, int]] = {}
-    for bsm in root:
-        oid = bsm.attrib.get("id", "?")
-        sm = bsm.find("SparseMatrix")
-        csr = sm.find("CompressedSparseRow")
-        nzpr = csr.find("NonzerosPerRow")
-        if nzpr is not None:
-            counts = np.array(nzpr.text.split(), dtype=np.int64)
-            rp = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
-        else:
-            rp = np.array(csr.find("RowStart").text.split(), dtype=np.int32)
-        ci = np.array(csr.find("ColumnIndex").text.split(), dtype=np.int32)
-        ind = sm.find("Indirection")
-        indirect = (np.array(ind.text.split(), dtype=np.int64) if ind is not None
-                    else np.arange(ci.size, dtype=np.int64))
-        dt = bsm.find("DataTensor")
-        scale = float(dt.attrib.get("scale", "1"))
-        is_complex = dt.attrib.get("type", "complex")[0].lower() == "c"
-        d = [int(v) for v in dt.attrib.get("dimensions", "0 0 0").split()]
-        raw = np.array((dt.text or "").split(), dtype=np.float64)
-        if is_complex:
-            raw = raw.reshape(d[0], d[1], d[2], 2)
-            src = raw[..., 0] + 1j*raw[..., 1]
-        else:
-            src = raw.reshape(d[0], d[1], d[2]).astype(np.complex128)
-        val = (src[indirect]*scale) if d[0] > 0 else np.zeros((ci.size, d[1], d[2]), np.complex128)
-        ops[oid[0]] = Bsr(rp, ci, val)
-        dims[oid[0]] = (d[1], d[2])
-    lm = dims["A"][1]
-    ln = dims["B"][1] if "B" in dims else dims["X"][1]
-    # values are stored [nnzb][slow][fast] exactly as in the file
-    return Problem(ops["A"], ops["X"], ops["B"], lm, ln, tol, path, X_exact=None)
+    (bench_tfqmrgpu.cu:153-157); here blocks are returned as stored, ``val[nnzb, dim1, dim2]``.
+    The parser (and the matching writers) live in ``formats.py``."""
+    from . import formats
+    return formats.read_xml_raw(path).to_problem(path)
 
 
 # ------------------------------------------------------------------------------------------------
