@@ -34,8 +34,9 @@ namespace tfq {
 
 namespace {
 
-constexpr int kConvWarps = 8, kConvThreads = 32*kConvWarps;   // converter warps; warp 8 issues copies and MMAs
-constexpr int kTcThreads = kConvThreads + 32;
+constexpr int kConvWarps = 8, kConvThreads = 32*kConvWarps;   // converter warps; warp 8 issues the MMAs, warp 9 the bulk copies of A
+constexpr int kMmaWarp = kConvWarps, kCopyWarp = kConvWarps + 1;
+constexpr int kTcThreads = kConvThreads + 64;
 // Tensor memory per CTA: [0, 2N): accumulator (main sum | correction sum), then two X operand stages of 2*LM columns (hi | lo).
 // LM = 16: 64 + 2*32 = 128 columns, LM = 32: 128 + 2*64 = 256 (two CTAs per SM), LM = 64: 256 + 2*128 = 512 (one CTA per SM)
 
@@ -216,6 +217,7 @@ spmm_tc_kernel(TcArgs const a)
     uint64_t *const bar_mma   = reinterpret_cast<uint64_t*>(smem_raw);      // [2]  MMAs of a stage have completed
     uint64_t *const bar_ready = bar_mma + 2;                                // [2]  a stage's operands are in place
     uint64_t *const bar_a     = bar_mma + 4;                                // [kRingA] raw A block has landed
+    uint64_t *const bar_free  = bar_a + kRingA;                             // [kRingA] the MMAs that read a ring slot have completed
     uint32_t *const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 128);
     uint32_t *const s_y = reinterpret_cast<uint32_t*>(smem_raw + 160);      // [G]
     unsigned char *const ring = smem_raw + 1024;                            // [kRingA][SLOT] A operands, hi and lo slabs interleaved
@@ -223,7 +225,7 @@ spmm_tc_kernel(TcArgs const a)
     int const tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     int const gs = a.gstride;
 
-    if (kConvWarps == w) tmem_alloc(tmem_slot, kTmemCols);
+    if (kMmaWarp == w) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -244,7 +246,7 @@ spmm_tc_kernel(TcArgs const a)
     int const nE = (nEu - pass*perPass < perPass) ? (nEu - pass*perPass) : perPass;
     bool const first_pass = (0 == pass);
 #ifdef TFQ_TC_TRACE
-    bool const trace_on = (0 == blockIdx.x) && (u == 3*gridDim.x) && (0 == lane) && (0 == w || 7 == w || kConvWarps == w);
+    bool const trace_on = (0 == blockIdx.x) && (u == 3*gridDim.x) && (0 == lane) && (0 == w || 7 == w || kMmaWarp == w);
     int const tslot0 = (0 == w) ? 0 : ((7 == w) ? 7 : 14);
 #endif
 
@@ -253,42 +255,50 @@ spmm_tc_kernel(TcArgs const a)
         mbar_init(&bar_mma[0], 1); mbar_init(&bar_mma[1], 1);
         mbar_init(&bar_ready[0], kConvWarps); mbar_init(&bar_ready[1], kConvWarps);
         #pragma unroll
-        for (int r = 0; r < kRingA; ++r) mbar_init(&bar_a[r], 1);
+        for (int r = 0; r < kRingA; ++r) { mbar_init(&bar_a[r], 1); mbar_init(&bar_free[r], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (kConvWarps == w) {
-        // ================= issuer warp: bulk copies of the A blocks and the MMAs =====================================
-        // The whole warp runs the loop converged and ONE elected lane issues: with elect.sync the compiler emits
-        // back-to-back UTCHMMA; a lane picked by "if (0 == lane)" costs an elect/branch loop (~125 cycles) per MMA.
-        uint32_t const leader = elect_one_sync();
+    if (kCopyWarp == w) {
+        // ================= copy warp: bulk copies of the A blocks into the ring ======================================
         // Entry indices are read by the whole warp, 32 entries at a time (lane l holds entry base + l): the elected lane then
-        // never waits on an index load in front of a copy (that wait was ~450 cycles per entry in the issuer's loop).
-        // (Requesting the entry's X blocks into L2 here - cp.async.bulk.prefetch.L2 - was measured: no gain, they hit L2 anyway.)
+        // never waits on an index load in front of a copy (that wait was ~450 cycles per entry when the MMA warp did this).
+        // (Requesting the entry's X blocks into L2 here - cp.async.bulk.prefetch.L2 - was measured: no gain, they hit L2 anyway;
+        // deriving the lo operands in this warp (on the stage barrier, or decoupled on a barrier per slot) or in two more warps
+        // of their own: 3.03-3.10 ms where this version takes 2.82 - the converter warps keep that work.)
+        // A slot is free again when the MMAs that read it have completed: its own barrier, because a parity wait cannot look
+        // two phases back and this warp may fall behind the stage barriers.
+        uint32_t const leader = elect_one_sync();
         uint32_t ia_l = 0;
-        auto fetch_a = [&](int e) {                 // called by the converged warp
+        for (int e = 0; e < nE; ++e) {
             if (0 == (e & 31)) ia_l = (e + lane < nE) ? a.ent_a[e0 + e + lane] : 0u;
             int const r = e % kRingA;
             uint32_t const ia = __shfl_sync(0xffffffffu, ia_l, e & 31);
+            if (e >= kRingA) mbar_wait(&bar_free[r], unsigned(((e / kRingA) - 1) & 1));
             if (leader) {
-                if (TFQ_TC_ABLATE & 16) { mbar_arrive(&bar_a[r]); return; }
-                mbar_expect_tx(&bar_a[r], unsigned(ABLK*sizeof(float)));
-                unsigned char const *src = reinterpret_cast<unsigned char const*>(a.A + size_t(ia)*ABLK);
-                #pragma unroll
-                for (int kq = 0; kq < LM/4; ++kq)      // one k-quad slab each, leaving room for the lo slab behind it
-                    bulk_g2s(ring + size_t(r)*SLOT + size_t(kq)*2*SLAB, src + size_t(kq)*SLAB, SLAB, &bar_a[r]);
+                if (TFQ_TC_ABLATE & 16) { mbar_arrive(&bar_a[r]); }
+                else {
+                    mbar_expect_tx(&bar_a[r], unsigned(ABLK*sizeof(float)));
+                    unsigned char const *src = reinterpret_cast<unsigned char const*>(a.A + size_t(ia)*ABLK);
+                    #pragma unroll
+                    for (int kq = 0; kq < LM/4; ++kq)      // one k-quad slab each, leaving room for the lo slab behind it
+                        bulk_g2s(ring + size_t(r)*SLOT + size_t(kq)*2*SLAB, src + size_t(kq)*SLAB, SLAB, &bar_a[r]);
+                }
             }
-        };
-        for (int e = 0; e < kRingA && e < nE; ++e) fetch_a(e);
+            __syncwarp();
+        }
+        // every arrival on the slot barriers must have happened before the barriers are invalidated at the end of the unit
+        // (the commits complete in order: the last one is enough)
+        if (nE > 0) mbar_wait(&bar_free[(nE - 1) % kRingA], unsigned(((nE - 1) / kRingA) & 1));
+    } else if (kMmaWarp == w) {
+        // ================= MMA warp =================================================================================
+        // The whole warp runs the loop converged and ONE elected lane issues: with elect.sync the compiler emits
+        // back-to-back UTCHMMA; a lane picked by "if (0 == lane)" costs an elect/branch loop (~125 cycles) per MMA.
+        uint32_t const leader = elect_one_sync();
         uint32_t const ring_u32 = smem_u32(ring);
         for (int e = 0; e < nE; ++e) {
             int const s = e & 1, r = e % kRingA;
-            TFQ_TRACE(e, 14);
-            if (e >= 2 && e - 2 + kRingA < nE) {                // ring slot of entry e-2 is free once its MMAs completed
-                mbar_wait(&bar_mma[s], unsigned(((e >> 1) - 1) & 1));
-                fetch_a(e - 2 + kRingA);
-            }
             TFQ_TRACE(e, 15);
             mbar_wait(&bar_ready[s], unsigned((e >> 1) & 1));   // X in TMEM, lo in shared memory (and the raw A landed)
             tc_fence_after();
@@ -305,7 +315,8 @@ spmm_tc_kernel(TcArgs const a)
                     mma_tf32_ts(tmem_base,     xa + 8*ks,      b, IDESC_2N, first);   // Xhi * [Ahi ; Alo]
                     mma_tf32_ts(tmem_base + N, xa + LM + 8*ks, b, IDESC_N,  1u);      // Xlo * Ahi
                 }
-                mma_commit(&bar_mma[s]);
+                mma_commit(&bar_mma[s]);       // the X stage is free again
+                mma_commit(&bar_free[r]);      // and so is the A slot
             }
             __syncwarp();
             TFQ_TRACE(e, 17);
@@ -437,13 +448,13 @@ spmm_tc_kernel(TcArgs const a)
     if (0 == tid) {
         mbar_inval(&bar_mma[0]); mbar_inval(&bar_mma[1]); mbar_inval(&bar_ready[0]); mbar_inval(&bar_ready[1]);
         #pragma unroll
-        for (int r = 0; r < kRingA; ++r) mbar_inval(&bar_a[r]);
+        for (int r = 0; r < kRingA; ++r) { mbar_inval(&bar_a[r]); mbar_inval(&bar_free[r]); }
     }
     } // passes
     } // units
     tc_fence_before();
     __syncthreads();
-    if (kConvWarps == w) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+    if (kMmaWarp == w) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
 
