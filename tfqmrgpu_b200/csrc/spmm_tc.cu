@@ -54,10 +54,17 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// global -> shared bulk copy (TMA engine without a tensor map), completion counted on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, void const *src_gmem, unsigned bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+// global -> shared bulk copy (TMA engine without a tensor map), completion counted on an mbarrier, with an L2 eviction policy
+// (createpolicy): the A stream is read once and must not displace the X blocks, which are re-read from L2 (27x for the stencil):
+// measured DRAM reads per launch 9.31 -> 8.40 GB, 2.77 -> 2.72 ms
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, void const *src_gmem, unsigned bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 __device__ __forceinline__ void mbar_inval(uint64_t *bar) {
     asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -270,6 +277,7 @@ spmm_tc_kernel(TcArgs const a)
         // A slot is free again when the MMAs that read it have completed: its own barrier, because a parity wait cannot look
         // two phases back and this warp may fall behind the stage barriers.
         uint32_t const leader = elect_one_sync();
+        uint64_t const stream_once = policy_evict_first();
         uint32_t ia_l = 0;
         for (int e = 0; e < nE; ++e) {
             if (0 == (e & 31)) ia_l = (e + lane < nE) ? a.ent_a[e0 + e + lane] : 0u;
@@ -283,7 +291,7 @@ spmm_tc_kernel(TcArgs const a)
                     unsigned char const *src = reinterpret_cast<unsigned char const*>(a.A + size_t(ia)*ABLK);
                     #pragma unroll
                     for (int kq = 0; kq < LM/4; ++kq)      // one k-quad slab each, leaving room for the lo slab behind it
-                        bulk_g2s(ring + size_t(r)*SLOT + size_t(kq)*2*SLAB, src + size_t(kq)*SLAB, SLAB, &bar_a[r]);
+                        bulk_g2s_hint(ring + size_t(r)*SLOT + size_t(kq)*2*SLAB, src + size_t(kq)*SLAB, SLAB, &bar_a[r], stream_once);
                 }
             }
             __syncwarp();
