@@ -317,11 +317,18 @@ def run_ours(args):
     spmm_avg_ms = spmm_ms/max(spmm_n, 1)
     achieved = spmm_bytes/(spmm_avg_ms*1e-3)*1e-9 if spmm_n else 0.0
     roofline = {"bound": "hbm", "kernel": "spmm (block-sparse product Y=A*X)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved/peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
+                "frac": achieved/peak, "traffic": traffic if (prec == "c" and (n, lm, ln, ncols) == (32, 32, 32, 2)) else None,
+                "peak_source": "measured" if peaks else "fallback",
                 "launches_timed": int(spmm_n), "avg_launch_ms": spmm_avg_ms, "algorithmic_bytes_per_launch": spmm_bytes,
                 "gflops_per_launch": spmm_flops*1e-9, "achieved_tflops": spmm_flops/(spmm_avg_ms*1e-3)*1e-12 if spmm_n else 0.0,
                 "share_of_step": spmm_ms/max(e0.elapsed_time(e1), 1e-9)}
 
+    if prec == "z" and spmm_n:
+        # complex fp64 (BASELINE configs 4/5): 64 flop/B and more, the product is bound by the FP64 (DMMA) pipe, not by HBM
+        tf = spmm_flops/(spmm_avg_ms*1e-3)*1e-12
+        roofline.update({"bound": "tensor", "achieved": tf, "peak": 37.0, "unit": "TFLOP/s", "frac": tf/37.0,
+                         "peak_source": "nominal B200 fp64 (MEASURED_PEAKS.json holds no fp64 figure)",
+                         "hbm_gbs_algorithmic": achieved})
     line = None
     if rank == 0:
         line = {
