@@ -165,7 +165,8 @@ __device__ __forceinline__ uint64_t smem_desc_noswizzle(uint32_t saddr, uint32_t
 
 
 // dev-only timing ablations (scripts/dev_ablate.sh builds variants; results are WRONG with any bit set):
-//   1 no lo(A) LDS/STS, 2 no split + tcgen05.st, 4 no X loads, 8 no MMAs (commit only), 16 no A bulk copies, 32 no Y stores
+//   1 no lo(A) LDS/STS, 2 no split + tcgen05.st, 4 no X loads, 8 no MMAs (commit only), 16 no A bulk copies, 32 no Y stores,
+//   128 no X path for every third entry (what sharing one X block between two block rows would save on the 27-point stencil)
 #ifndef TFQ_TC_ABLATE
 #define TFQ_TC_ABLATE 0
 #endif
@@ -338,8 +339,8 @@ spmm_tc_kernel(TcArgs const a)
         bool const has_g = (g < gs) && (kNoBlock != iy);
         uint32_t const xoff = uint32_t(cx)*LM*LN + uint32_t(KH*h)*LN + uint32_t(j);
         auto x_index = [&](int e) -> uint32_t { return (has_g && e < nE) ? a.ent_x[size_t(e0 + e)*gs + g] : kNoBlock; };
-        auto load_x = [&](uint32_t ix, float (&xr)[KH]) {
-            if (kNoBlock != ix && !(TFQ_TC_ABLATE & 4)) {
+        auto load_x = [&](uint32_t ix, float (&xr)[KH], bool skip = false) {
+            if (kNoBlock != ix && !(TFQ_TC_ABLATE & 4) && !skip) {
                 float const *xp = a.x + size_t(ix)*XBLK + xoff;
                 #pragma unroll
                 for (int r = 0; r < KH; ++r) xr[r] = __ldg(xp + r*LN);
@@ -355,7 +356,7 @@ spmm_tc_kernel(TcArgs const a)
             // the ~100 cycles a try_wait takes on an already completed barrier overlap with the load issue
             bool const stage_free = (e < 2) || mbar_try_wait(&bar_mma[s], unsigned(((e >> 1) - 1) & 1));
             bool const a_landed = mbar_try_wait(&bar_a[r], unsigned((e / kRingA) & 1));
-            load_x(ix_next, xn);
+            load_x(ix_next, xn, (TFQ_TC_ABLATE & 128) && ((e + 1) % 3 == 2));
             ix_next2 = x_index(e + 2);
             TFQ_TRACE(e, tslot0 + 1);
             if (e >= 2) { if (!stage_free) mbar_wait(&bar_mma[s], unsigned(((e >> 1) - 1) & 1)); tc_fence_after(); } // stage s is free again
@@ -365,7 +366,7 @@ spmm_tc_kernel(TcArgs const a)
                 uint32_t const t0 = tmem_base + (uint32_t(32*q) << 16) + kTmemStage0 + uint32_t(s)*kStageCols + uint32_t(KH*h);
                 constexpr int W = (KH < 16) ? KH : 16;             // columns per tcgen05.st
                 #pragma unroll
-                for (int c = 0; c < ((TFQ_TC_ABLATE & 2) ? 0 : KH/W); ++c) {
+                for (int c = 0; c < (((TFQ_TC_ABLATE & 2) || ((TFQ_TC_ABLATE & 128) && e % 3 == 2)) ? 0 : KH/W); ++c) {
                     uint32_t hi[W], lo[W];
                     #pragma unroll
                     for (int t = 0; t < W; ++t) split_rn(xc[W*c + t], hi[t], lo[t]);
