@@ -32,7 +32,8 @@ tfqmrgpuStatus_t tfqmrgpux_setVerbosity(int level);
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_getPlanArray(tfqmrgpuBsrsvPlan_t plan, int kind, void *out, size_t *count);
 
 /* info[0..15] = nnzbX, nnzbB, nnzbA, nCols, nPairs, LM, LN, precision char, number of vector tiles,
- * number of SpMM units, SpMM columns per unit, SpMM entries, mb, 1 if the tcgen05 (fp32) product is used, 1 if the DMMA (fp64) product is used, 0 */
+ * number of SpMM units, SpMM columns per unit, SpMM entries, mb, 1 if the tcgen05 (fp32) product is used, 1 if the DMMA (fp64) product is used,
+ * 1 if the small-block (LM <= 8) register-staged product is used */
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_getPlanInfo(tfqmrgpuBsrsvPlan_t plan, int64_t info[16]);
 
 /* Random shadow vector v3, float[nnzbX][2][LM][LN] in the caller's X block order (= the layout the

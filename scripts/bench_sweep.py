@@ -11,8 +11,11 @@ from tfqmrgpu_b200 import api, synthetic, _lib as L
 
 ALLOWED = [(4, 4), (4, 5), (4, 8), (4, 32), (8, 8), (8, 9), (8, 10), (8, 32), (8, 64), (16, 16), (16, 32), (16, 64), (32, 32), (32, 64), (64, 64)]
 n = int(os.environ.get("N", "12"))
+max_lm = int(os.environ.get("MAX_LM", "64"))      # e.g. MAX_LM=8: only the small-block kernel's sizes
 rows = []
 for lm, ln in ALLOWED:
+    if lm > max_lm:
+        continue
     ncols = max(1, 64//ln)
     for prec, dt, sigma, tol in (("c", np.float32, 8.0, 1e-3), ("z", np.float64, 1.0, 1e-9)):
         es = 4 if prec == "c" else 8
@@ -33,7 +36,7 @@ for lm, ln in ALLOWED:
         sp_ms = prof["spmm_ms"]/max(prof["spmm_launches"], 1)
         flops = nP*8*lm*lm*ln
         nbytes = sp.nnzbA*2*lm*lm*es + 2*info["nnzbX"]*2*lm*ln*es + 8*nP + 4*(info["nnzbX"] + 1)
-        rows.append(dict(lm=lm, ln=ln, prec=prec, kernel="dmma" if info["use_dmma"] else ("tcgen05" if info["use_tc"] else "simt"),
+        rows.append(dict(lm=lm, ln=ln, prec=prec, kernel="dmma" if info["use_dmma"] else ("tcgen05" if info["use_tc"] else ("simt-small" if info.get("use_small") else "simt")),
                          status=int(st), iterations=res["iterations"], residual=res["residuum"], solve_ms=ms,
                          ms_per_iteration=ms/max(res["iterations"], 1), spmm_us=1e3*sp_ms,
                          spmm_gflops=flops/sp_ms*1e-6 if sp_ms else 0, spmm_gbs=nbytes/sp_ms*1e-6 if sp_ms else 0))

@@ -162,7 +162,7 @@ class BsrsvPlan:
         info = (C.c_int64*16)()
         _check(self.lib.tfqmrgpux_bsrsv_getPlanInfo(self.plan, info), "getPlanInfo")
         keys = ["nnzbX", "nnzbB", "nnzbA", "nCols", "nPairs", "LM", "LN", "precision", "nTiles", "nUnits", "gmax",
-                "nEntries", "mb", "use_tc", "use_dmma"]
+                "nEntries", "mb", "use_tc", "use_dmma", "use_small"]
         return {k: int(info[i]) for i, k in enumerate(keys)}
 
     def set_v3(self, v3, on_device=False):

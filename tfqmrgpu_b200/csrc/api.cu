@@ -441,7 +441,7 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getPlanInfo(tfqmrgpuBsrsvPlan_t plan, int64_t i
     if (nullptr == plan || nullptr == info) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     Plan const &p = *P(plan);
     int64_t const v[16] = {p.nnzbX, p.nnzbB, p.nnzbA, int64_t(p.nCols), int64_t(p.nPairs), p.LM, p.LN, p.precision,
-                           int64_t(p.nTiles), int64_t(p.nUnits), int64_t(p.gmax), int64_t(p.nEntries), p.mb, int64_t(p.use_tc), int64_t(p.use_dmma), 0};
+                           int64_t(p.nTiles), int64_t(p.nUnits), int64_t(p.gmax), int64_t(p.nEntries), p.mb, int64_t(p.use_tc), int64_t(p.use_dmma), int64_t(p.use_small)};
     std::memcpy(info, v, sizeof(v));
     return TFQMRGPU_STATUS_SUCCESS;
 }

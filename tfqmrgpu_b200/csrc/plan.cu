@@ -374,7 +374,15 @@ tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, ch
     {
         int const TI = spmm_ti(is_double, LM, LN), TJ = spmm_tj(is_double, LN);
         // aim at ~128 threads per CTA: threads = (LM/TI) * (g*LN/TJ)
-        int g = std::max(1, (128*TI*TJ)/(LM*LN));
+        // LM <= 8, measured on the block-size sweep (1728 block rows, 64 RHS columns) and the FD example: the small-block
+        // kernel (4 entry groups of <= 32 threads, spmm.cu) wins in fp32 (4x4: 55 vs 97 us, 8x8: 95 vs 141 us; not at LN = 9)
+        // and for tiny fp64 units (FD_problem.xml, one 8x8 block column: 3.0 vs 3.5 ms per solve); wide fp64 units stay on the ring
+        {
+            char const *env_small = std::getenv("TFQMRGPU_SMALL");
+            bool const allowed = env_small ? (0 != std::atoi(env_small)) : true;
+            p.use_small = allowed && (LM <= 8) && (is_double ? (p.maxColsPerRow*LN <= 16) : (9 != LN));
+        }
+        int g = std::max(1, ((p.use_small ? 32 : 128)*TI*TJ)/(LM*LN));
         g = std::min(g, 16);
         g = std::min(g, p.maxColsPerRow);
         // keep one pipeline stage (A block + g X blocks, possibly k-chunked) reasonable: <= 48 KiB at 4 k-rows
