@@ -346,7 +346,12 @@ tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, ch
     {
         size_t const target = size_t(nsm)*4;
         size_t tb = std::max<size_t>(1, (size_t(p.nnzbX) + target - 1)/target);
-        size_t const tb_min = std::max<size_t>(1, (16*1024 + blockBytes - 1)/blockBytes);
+        char const *env_tile = std::getenv("TFQMRGPU_TILE_KB");      // dev switch: minimum bytes of one vector per tile
+        // 16 KiB of a vector per tile, 4 KiB when that would leave SMs without a tile (FD_problem.xml, 175 KB per vector:
+        // 2.98 -> 2.64 ms per solve; on the 1728-row sweep 16 KiB is the better one)
+        size_t const vec_bytes = size_t(p.nnzbX)*blockBytes;
+        size_t const tile_kb = env_tile ? size_t(std::max(1, std::atoi(env_tile))) : ((vec_bytes/(16*1024) < size_t(nsm)) ? 4 : 16);
+        size_t const tb_min = std::max<size_t>(1, (tile_kb*1024 + blockBytes - 1)/blockBytes);
         tb = std::max(tb, tb_min);
         std::vector<Tile> tiles;
         std::vector<uint32_t> coltile(size_t(nb) + 1, 0);
