@@ -159,6 +159,37 @@ def test_spmm_every_block_size(lmln, prec):
     assert np.abs(Y - Yo).max() <= tol
 
 
+@pytest.mark.parametrize("lm,ln,prec,ncols,expect_small", [(4, 4, "c", 24, 1), (8, 8, "c", 20, 1), (4, 5, "c", 7, 1), (8, 10, "c", 3, 1),
+                                                             (8, 8, "z", 1, 1), (4, 4, "z", 3, 1), (8, 8, "z", 5, 0), (8, 9, "c", 4, 0)])
+def test_small_block_product_long_rows_and_ragged_units(lm, ln, prec, ncols, expect_small):
+    """spmm_small_kernel (LM <= 8): rows with more entries than the kernel's shared-memory index cache (70 > 64), several
+    batches, units with absent block columns, more block columns than one unit holds; and which plans select it."""
+    mb = 70
+    prob = P.random_system(mb, lm, ln, ncols=ncols, pA=1.0, pX=.6, seed=lm*10 + ln, unsorted=True)
+    h = api.Handle()
+    pl = api.BsrsvPlan(h, prob.mb, prob.A.rowptr, prob.A.colind, prob.X.rowptr, prob.X.colind, prob.X.rowptr, prob.X.colind)
+    pl.buffer_size_for(lm, ln, prec)
+    info = pl.plan_info()
+    assert info["use_small"] == expect_small
+    # several batches per unit everywhere; with many block columns the merged entry lists outgrow the index cache (64)
+    assert info["nEntries"] >= (65 if ncols >= 20 else 25)*info["nUnits"]
+    pl.close(); h.close()
+    A, X, Y, lists = _spmm_case(prob.mb, prob.A.rowptr, prob.A.colind, prob.X.rowptr, prob.X.colind, lm, ln, prec)
+    Yo = O.multiply(A, X, lists["starts"], lists["pairs"], lm, ln)
+    tol = 2e-4 if prec == "c" else 1e-12*prob.mb*lm*2
+    assert np.abs(Y - Yo).max() <= tol
+
+
+def test_small_block_switch(monkeypatch):
+    monkeypatch.setenv("TFQMRGPU_SMALL", "0")
+    prob = P.random_system(12, 4, 4, seed=5)
+    h = api.Handle()
+    pl = api.BsrsvPlan(h, prob.mb, prob.A.rowptr, prob.A.colind, prob.X.rowptr, prob.X.colind, prob.X.rowptr, prob.X.colind)
+    pl.buffer_size_for(4, 4, "c")
+    assert pl.plan_info()["use_small"] == 0
+    pl.close(); h.close()
+
+
 # ---- full solves ------------------------------------------------------------------------------------------
 def _solve_case(prob, prec, tol, maxit, tA, tB, v3=None, index_offset=0):
     dt = np.float64 if prec == "z" else np.float32
