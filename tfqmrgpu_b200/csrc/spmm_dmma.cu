@@ -49,6 +49,9 @@ __device__ __forceinline__ bool mbar_try_wait_d(uint64_t *bar, unsigned parity) 
 __device__ __forceinline__ void mbar_wait_d(uint64_t *bar, unsigned parity) {
     for (uint32_t spins = 0; !mbar_try_wait_d(bar, parity); ++spins) if (spins > (1u << 24)) __trap();
 }
+__device__ __forceinline__ void mbar_arrive_d(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32d(bar)) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s_d(void *dst_smem, void const *src_gmem, unsigned bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32d(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32d(bar)) : "memory");
@@ -71,7 +74,8 @@ spmm_dmma_kernel(DmmaArgs const a)
     if (a.expect >= 0 && a.ctl->state != a.expect) return; // device-resident solver control
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t *const bars = reinterpret_cast<uint64_t*>(smem_raw);          // [stages]
+    uint64_t *const bars = reinterpret_cast<uint64_t*>(smem_raw);          // [stages] slab landed
+    uint64_t *const bars_free = bars + kMaxStagesD;                        // [stages] all warps of the CTA are done reading it
     double *const stage0 = reinterpret_cast<double*>(smem_raw + 128);
     __shared__ uint32_t s_y[16];
     __shared__ int s_ng;
@@ -95,7 +99,7 @@ spmm_dmma_kernel(DmmaArgs const a)
         for (int q = tid; q < nC*G; q += blockDim.x) s_ent_x[q] = a.ent_x[size_t(e0)*G + q];
     }
     if (0 == tid) {
-        for (int s = 0; s < nStages; ++s) mbar_init_d(&bars[s], 1);
+        for (int s = 0; s < nStages; ++s) { mbar_init_d(&bars[s], 1); mbar_init_d(&bars_free[s], blockDim.x >> 5); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -141,11 +145,15 @@ spmm_dmma_kernel(DmmaArgs const a)
     if (w == 0) for (int st = 0; st < nStages - 1 && st < nSteps; ++st) issue(st);
 
     int const fr = lane >> 2, fk = lane & 3;        // fragment coordinates of this lane
+    // LM >= 32: no CTA-wide barrier per step (it was 15 % of the stall samples at 32x32; config-4 shard 30.97 -> 29.59 ms per
+    // product); at LM = 16 the steps are too short for the extra arrive/wait to pay (262 -> 279 us on the sweep): __syncthreads
+    constexpr bool kFreeBars = (LM >= 32);
     for (int st = 0; st < nSteps; ++st) {
         int const s = st % nStages;
-        if (w == 0 && st + nStages - 1 < nSteps) issue(st + nStages - 1);   // that slot was drained at the end of step st-1
+        if (!kFreeBars && w == 0 && st + nStages - 1 < nSteps) issue(st + nStages - 1);   // that slot was drained at the end of step st-1
+        // every warp waits for the slab, also one without columns: it must not run ahead and report a slot free twice in one phase
+        mbar_wait_d(&bars[s], unsigned((st/nStages) & 1));
         if (warp_active) {
-            mbar_wait_d(&bars[s], unsigned((st/nStages) & 1));
             double const *const As_re = stage0 + size_t(s)*stageElems;
             double const *const As_im = As_re + kKC*SA;
             double const *const Xs = As_re + 2*kKC*SA;
@@ -174,7 +182,18 @@ spmm_dmma_kernel(DmmaArgs const a)
                 }
             }
         }
-        __syncthreads(); // everyone is done with stage s before it is refilled
+        if (kFreeBars) {
+            // every warp reports the stage free, and the producer warp - after its own share of step st - refills the slot of
+            // step st-1 once all warps have left it
+            __syncwarp();
+            if (0 == lane) mbar_arrive_d(&bars_free[s]);
+            if (w == 0 && st + nStages - 1 < nSteps) {
+                if (st >= 1) mbar_wait_d(&bars_free[(st - 1) % nStages], unsigned(((st - 1)/nStages) & 1));
+                issue(st + nStages - 1);
+            }
+        } else {
+            __syncthreads(); // everyone is done with stage s before it is refilled
+        }
     }
 
     if (warp_active) {
