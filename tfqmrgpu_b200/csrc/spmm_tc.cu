@@ -180,7 +180,7 @@ __device__ long long g_tc_trace[64*24];
 #endif
 
 template <int LM> struct TcShape {
-    static constexpr int ring = (64 == LM) ? 3 : ((32 == LM) ? 5 : 6); // A blocks in flight per CTA (bulk-copy ring)
+    static constexpr int ring = (64 == LM) ? 3 : 6;                    // A blocks in flight per CTA (bulk-copy ring)
     static constexpr int ctas = (64 == LM) ? 1 : 2;                    // resident CTAs per SM (TMEM columns)
     static constexpr uint32_t acc_cols = 4*LM, stage_cols = 2*LM;      // accumulator (2N), one X stage (hi | lo)
     static constexpr uint32_t tmem_cols = (acc_cols + 2*stage_cols <= 128) ? 128 : ((acc_cols + 2*stage_cols <= 256) ? 256 : 512);
@@ -226,40 +226,22 @@ spmm_tc_kernel(TcArgs const a)
     uint64_t *const bar_ready = bar_mma + 2;                                // [2]  a stage's operands are in place
     uint64_t *const bar_a     = bar_mma + 4;                                // [kRingA] raw A block has landed
     uint64_t *const bar_free  = bar_a + kRingA;                             // [kRingA] the MMAs that read a ring slot have completed
-    uint64_t *const bar_acc   = bar_free + kRingA;                          // [1]  the epilogue has read the accumulators
-    uint32_t *const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 192);
+    uint32_t *const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 128);
+    uint32_t *const s_y = reinterpret_cast<uint32_t*>(smem_raw + 160);      // [G]
     unsigned char *const ring = smem_raw + 1024;                            // [kRingA][SLOT] A operands, hi and lo slabs interleaved
-    float *const exch = reinterpret_cast<float*>(ring + size_t(kRingA)*SLOT);   // [G][2][EC][LN] floats: Re <-> Im exchange of the epilogue
 
     int const tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     int const gs = a.gstride;
 
     if (kMmaWarp == w) tmem_alloc(tmem_slot, kTmemCols);
-    if (0 == tid) {
-        mbar_init(&bar_mma[0], 1); mbar_init(&bar_mma[1], 1);
-        mbar_init(&bar_ready[0], kConvWarps); mbar_init(&bar_ready[1], kConvWarps);
-        #pragma unroll
-        for (int r = 0; r < kRingA; ++r) { mbar_init(&bar_a[r], 1); mbar_init(&bar_free[r], 1); }
-        mbar_init(bar_acc, kConvWarps);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t const tmem_base = *tmem_slot;
 
-    // persistent: two resident CTAs per SM walk the units; TMEM is allocated once (a gated-off launch of this kernel then costs
-    // a handful of CTAs instead of one per unit).  The barriers live across units: every role counts the entries (tb) and the
-    // (unit, pass) segments (nb) it has been through, and derives stage, ring slot and phase parities from these counters, so
-    // the three roles only meet at the barriers - the copy warp already fetches the next unit's A blocks during the epilogue.
-    uint32_t tb = 0, nb = 0;
-    // converter warps: Y block of this thread's block column, read one unit ahead (no load latency at the start of a unit)
-    int const cg = (32*(w & 3) + lane)/(2*LN);
-    auto unit_y_of = [&](uint32_t uu) -> uint32_t { return (w < kConvWarps && uu < a.nUnits && cg < gs) ? a.unit_y[size_t(uu)*gs + cg] : kNoBlock; };
-    uint32_t iy_next = unit_y_of(blockIdx.x);
+    // persistent: two resident CTAs per SM walk the units; TMEM is allocated once, the barriers are re-armed per unit
+    // (a gated-off launch of this kernel then costs a handful of CTAs instead of one per unit)
     for (uint32_t u = blockIdx.x; u < a.nUnits; u += gridDim.x) {
-    uint32_t const iy_unit = iy_next;
-    iy_next = unit_y_of(u + gridDim.x);
     uint32_t const e0u = a.unit_e0[u];
     int const nEu = int(a.unit_e0[u + 1] - e0u);
     // Accumulation chains are cut into passes of at most kChain entries: the tensor core truncates the fp32 accumulator
@@ -276,7 +258,15 @@ spmm_tc_kernel(TcArgs const a)
     int const tslot0 = (0 == w) ? 0 : ((7 == w) ? 7 : 14);
 #endif
 
-    uint32_t const tb0 = tb;        // entries of this CTA before the segment
+    if (tid < G) s_y[tid] = (tid < gs) ? a.unit_y[size_t(u)*gs + tid] : kNoBlock;
+    if (0 == tid) {
+        mbar_init(&bar_mma[0], 1); mbar_init(&bar_mma[1], 1);
+        mbar_init(&bar_ready[0], kConvWarps); mbar_init(&bar_ready[1], kConvWarps);
+        #pragma unroll
+        for (int r = 0; r < kRingA; ++r) { mbar_init(&bar_a[r], 1); mbar_init(&bar_free[r], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     if (kCopyWarp == w) {
         // ================= copy warp: bulk copies of the A blocks into the ring ======================================
@@ -292,10 +282,9 @@ spmm_tc_kernel(TcArgs const a)
         uint32_t ia_l = 0;
         for (int e = 0; e < nE; ++e) {
             if (0 == (e & 31)) ia_l = (e + lane < nE) ? a.ent_a[e0 + e + lane] : 0u;
-            uint32_t const t = tb0 + uint32_t(e);
-            int const r = int(t % kRingA);
+            int const r = e % kRingA;
             uint32_t const ia = __shfl_sync(0xffffffffu, ia_l, e & 31);
-            if (t >= uint32_t(kRingA)) mbar_wait(&bar_free[r], unsigned(((t / kRingA) - 1) & 1));
+            if (e >= kRingA) mbar_wait(&bar_free[r], unsigned(((e / kRingA) - 1) & 1));
             if (leader) {
                 if (TFQ_TC_ABLATE & 16) { mbar_arrive(&bar_a[r]); }
                 else {
@@ -308,18 +297,19 @@ spmm_tc_kernel(TcArgs const a)
             }
             __syncwarp();
         }
+        // every arrival on the slot barriers must have happened before the barriers are invalidated at the end of the unit
+        // (the commits complete in order: the last one is enough)
+        if (nE > 0) mbar_wait(&bar_free[(nE - 1) % kRingA], unsigned(((nE - 1) / kRingA) & 1));
     } else if (kMmaWarp == w) {
         // ================= MMA warp =================================================================================
         // The whole warp runs the loop converged and ONE elected lane issues: with elect.sync the compiler emits
         // back-to-back UTCHMMA; a lane picked by "if (0 == lane)" costs an elect/branch loop (~125 cycles) per MMA.
         uint32_t const leader = elect_one_sync();
         uint32_t const ring_u32 = smem_u32(ring);
-        if (nb >= 1) { mbar_wait(bar_acc, unsigned((nb - 1) & 1)); tc_fence_after(); }   // the previous segment's sums have been read
         for (int e = 0; e < nE; ++e) {
-            uint32_t const t = tb0 + uint32_t(e);
-            int const s = int(t & 1), r = int(t % kRingA);
+            int const s = e & 1, r = e % kRingA;
             TFQ_TRACE(e, 15);
-            mbar_wait(&bar_ready[s], unsigned((t >> 1) & 1));   // X in TMEM, lo in shared memory (and the raw A landed)
+            mbar_wait(&bar_ready[s], unsigned((e >> 1) & 1));   // X in TMEM, lo in shared memory (and the raw A landed)
             tc_fence_after();
             TFQ_TRACE(e, 16);
             if (leader) {
@@ -345,7 +335,7 @@ spmm_tc_kernel(TcArgs const a)
         int const q = w & 3, h = w >> 2;
         int const m = 32*q + lane;
         int const g = m/(2*LN), cx = (m/LN) & 1, j = m % LN;
-        uint32_t const iy = iy_unit;
+        uint32_t const iy = s_y[g];
         bool const has_g = (g < gs) && (kNoBlock != iy);
         uint32_t const xoff = uint32_t(cx)*LM*LN + uint32_t(KH*h)*LN + uint32_t(j);
         auto x_index = [&](int e) -> uint32_t { return (has_g && e < nE) ? a.ent_x[size_t(e0 + e)*gs + g] : kNoBlock; };
@@ -361,16 +351,15 @@ spmm_tc_kernel(TcArgs const a)
         };
         // one entry: xc holds its X values; the loads of entry e+1 go to xn while entry e is split
         auto step = [&](int e, float (&xc)[KH], float (&xn)[KH], uint32_t ix_next, uint32_t &ix_next2) {
-            uint32_t const t = tb0 + uint32_t(e);
-            int const s = int(t & 1), r = int(t % kRingA);
+            int const s = e & 1, r = e % kRingA;
             TFQ_TRACE(e, tslot0 + 0);
             // the ~100 cycles a try_wait takes on an already completed barrier overlap with the load issue
-            bool const stage_free = (t < 2) || mbar_try_wait(&bar_mma[s], unsigned(((t >> 1) - 1) & 1));
-            bool const a_landed = mbar_try_wait(&bar_a[r], unsigned((t / kRingA) & 1));
+            bool const stage_free = (e < 2) || mbar_try_wait(&bar_mma[s], unsigned(((e >> 1) - 1) & 1));
+            bool const a_landed = mbar_try_wait(&bar_a[r], unsigned((e / kRingA) & 1));
             load_x(ix_next, xn, (TFQ_TC_ABLATE & 128) && ((e + 1) % 3 == 2));
             ix_next2 = x_index(e + 2);
             TFQ_TRACE(e, tslot0 + 1);
-            if (t >= 2) { if (!stage_free) mbar_wait(&bar_mma[s], unsigned(((t >> 1) - 1) & 1)); tc_fence_after(); } // stage s is free again
+            if (e >= 2) { if (!stage_free) mbar_wait(&bar_mma[s], unsigned(((e >> 1) - 1) & 1)); tc_fence_after(); } // stage s is free again
             TFQ_TRACE(e, tslot0 + 2);
             // ---- X operand: split, registers -> tensor memory (lane = m, column = k) ------------------------
             {
@@ -387,7 +376,7 @@ spmm_tc_kernel(TcArgs const a)
             }
             // ---- A operand: hi = the raw block in the ring, lo = a - trunc(a) -> shared memory ------------------
             TFQ_TRACE(e, tslot0 + 3);
-            if (!a_landed) mbar_wait(&bar_a[r], unsigned((t / kRingA) & 1));
+            if (!a_landed) mbar_wait(&bar_a[r], unsigned((e / kRingA) & 1));
             TFQ_TRACE(e, tslot0 + 4);
             {
                 unsigned char *const slot = ring + size_t(r)*SLOT;
@@ -420,12 +409,12 @@ spmm_tc_kernel(TcArgs const a)
                 else break;
             }
             // all MMAs complete when the last commit has arrived (they retire in order)
-            uint32_t const tl = tb0 + uint32_t(nE - 1);
-            mbar_wait(&bar_mma[tl & 1], unsigned((tl >> 1) & 1));
+            mbar_wait(&bar_mma[(nE - 1) & 1], unsigned(((nE - 1) >> 1) & 1));
             tc_fence_after();
         }
 
         // ---- epilogue: D -> registers, combine the four real products, store Y ---------------------------------
+        float *const exch = reinterpret_cast<float*>(ring);   // [G][2][EC][LN] floats, aliases the A ring (all copies and MMAs are done)
         constexpr int EC = (LM < 32) ? LM : 32;              // accumulator columns per pass
         #pragma unroll 1
         for (int c = 0; c < LM/EC; ++c) {
@@ -459,18 +448,19 @@ spmm_tc_kernel(TcArgs const a)
                     for (int i = 0; i < EC; ++i) yp[i*LN] += __uint_as_float(d[i]);
                 }
             }
-            asm volatile("bar.sync 1, %0;" :: "n"(kConvThreads) : "memory");   // exch is reused (next column pass or next segment)
+            if (c + 1 < LM/EC) asm volatile("bar.sync 1, %0;" :: "n"(kConvThreads) : "memory");   // exch is reused
         }
-        // the accumulators may be overwritten by the next segment's first MMA
-        tc_fence_before();
-        __syncwarp();
-        if (0 == lane) mbar_arrive(bar_acc);
     }
-    tb += uint32_t(nE); nb += 1;
+    tc_fence_before();
+    __syncthreads();          // everyone is done with this unit's accumulator, ring and barriers
+    tc_fence_after();
+    if (0 == tid) {
+        mbar_inval(&bar_mma[0]); mbar_inval(&bar_mma[1]); mbar_inval(&bar_ready[0]); mbar_inval(&bar_ready[1]);
+        #pragma unroll
+        for (int r = 0; r < kRingA; ++r) { mbar_inval(&bar_a[r]); mbar_inval(&bar_free[r]); }
+    }
     } // passes
     } // units
-    // every asynchronous arrival on a barrier of this CTA must have happened before it exits (the commits complete in order)
-    if (kCopyWarp == w && tb > 0) mbar_wait(&bar_free[(tb - 1) % kRingA], unsigned(((tb - 1) / kRingA) & 1));
     tc_fence_before();
     __syncthreads();
     if (kMmaWarp == w) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
@@ -481,8 +471,7 @@ template <int LM, int LN>
 tfqmrgpuStatus_t launch_tc(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream)
 {
     constexpr int ring = TcShape<LM>::ring, ctas = TcShape<LM>::ctas;
-    constexpr size_t exch = size_t(64/LN)*2*((LM < 32) ? LM : 32)*LN*sizeof(float);   // epilogue exchange buffer
-    constexpr size_t smem = 1024 + ring*2*size_t(2*LM*LM)*sizeof(float) + exch + 1024; // barriers + A ring (hi and lo slabs) + exchange
+    constexpr size_t smem = 1024 + ring*2*size_t(2*LM*LM)*sizeof(float) + 1024; // barriers + A ring (hi and lo slabs)
     // `ctas` CTAs per SM by their TMEM columns: pad the request so that one more CTA can never be resident
     constexpr size_t smem_min = (2 == ctas) ? 80*1024 : 120*1024;
     constexpr size_t smem_req = (smem < smem_min) ? smem_min : smem;
