@@ -17,7 +17,7 @@ assert 0 == lib.tfq_tc_trace_dump(buf.ctypes.data_as(ctypes.c_void_p), buf.size)
 t = buf.reshape(64, 24)
 ne = int((t[:, 0] != 0).sum()); t = t[:ne]; t0 = t[t != 0].min()
 names = ['c0.start', 'c0.ldx', 'c0.stage', 'c0.split', 'c0.A', 'c0.lo', 'c0.ready', 'c7.start', 'c7.ldx', 'c7.stage', 'c7.split', 'c7.A', 'c7.lo', 'c7.ready',
-         'i.top', 'i.refill', 'i.ready', 'i.issued']
+         '-', 'm.top', 'm.ready', 'm.issued']      # MMA warp: loop top, stage barrier passed, 8 MMAs + commits issued (the copy warp is not traced)
 print('entry ' + ' '.join(f'{s:>9s}' for s in names))
 for e in range(ne):
     print(f'{e:5d} ' + ' '.join(f'{int(t[e, k] - t0) if t[e, k] else -1:9d}' for k in range(18)))
