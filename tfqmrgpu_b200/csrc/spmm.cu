@@ -245,11 +245,8 @@ tfqmrgpuStatus_t launch_typed(Plan const &p, void *y, void const *x, int expect,
     if (threads > 256) return TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED);
 
     auto kernel = spmm_unit_kernel<real_t, LM, LN, TI, TJ>;
-    static size_t configured = 0; // per instantiation
-    if (smem > configured) {
-        TFQ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        configured = smem;
-    }
+    static size_t configured[kMaxDevices] = {0}; // per instantiation and device
+    TFQ_CUDA(ensure_dynamic_smem(kernel, smem, configured));
     SpmmArgs<real_t> a;
     a.y = static_cast<real_t*>(y); a.x = static_cast<real_t const*>(x);
     a.A = ws<real_t const>(p, p.off_A); a.zero = ws<real_t const>(p, p.off_zero);
@@ -458,11 +455,8 @@ tfqmrgpuStatus_t launch_small(Plan const &p, void *y, void const *x, int expect,
     size_t const part = size_t(kSplit - 1)*T*2*TI*TJ*sizeof(real_t);
     size_t const smem = std::max(2*size_t(eb)*entrySlot*16, part);
     auto kernel = spmm_small_kernel<real_t, LM, LN, TI, TJ>;
-    static size_t configured = 0; // per instantiation
-    if (smem > configured) {
-        TFQ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        configured = smem;
-    }
+    static size_t configured[kMaxDevices] = {0}; // per instantiation and device
+    TFQ_CUDA(ensure_dynamic_smem(kernel, smem, configured));
     SpmmArgs<real_t> a;
     a.y = static_cast<real_t*>(y); a.x = static_cast<real_t const*>(x);
     a.A = ws<real_t const>(p, p.off_A); a.zero = ws<real_t const>(p, p.off_zero);

@@ -223,11 +223,8 @@ tfqmrgpuStatus_t launch_d(Plan const &p, void *y, void const *x, int expect, cud
     int const warps = (LM/16)*((G*LN + 31)/32);
     if (warps > 8 || warps < 1) return TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED);
     auto kernel = spmm_dmma_kernel<LM, LN>;
-    static size_t configured = 0;
-    if (smem > configured) {
-        TFQ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        configured = smem;
-    }
+    static size_t configured[kMaxDevices] = {0}; // per instantiation and device
+    TFQ_CUDA(ensure_dynamic_smem(kernel, smem, configured));
     DmmaArgs a;
     a.y = static_cast<double*>(y); a.x = static_cast<double const*>(x);
     a.A = ws<double const>(p, p.off_A); a.zero = ws<double const>(p, p.off_zero);

@@ -476,17 +476,16 @@ tfqmrgpuStatus_t launch_tc(Plan const &p, void *y, void const *x, int expect, cu
     constexpr size_t smem_min = (2 == ctas) ? 80*1024 : 120*1024;
     constexpr size_t smem_req = (smem < smem_min) ? smem_min : smem;
     auto kernel = spmm_tc_kernel<LM, LN>;
-    static bool configured = false;
-    if (!configured) {
-        TFQ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_req)));
-        configured = true;
-    }
+    static size_t configured[kMaxDevices] = {0}; // per instantiation and device
+    TFQ_CUDA(ensure_dynamic_smem(kernel, smem_req, configured));
     TcArgs a;
     a.y = static_cast<float*>(y); a.x = static_cast<float const*>(x); a.A = ws<float const>(p, p.off_A);
     a.unit_e0 = p.d_unit_e0; a.unit_y = p.d_unit_y; a.ent_a = p.d_ent_a; a.ent_x = p.d_ent_x;
     a.ctl = ws<Control const>(p, p.off_ctl); a.expect = expect; a.gstride = int(p.gmax); a.nUnits = p.nUnits;
-    static int num_sms = 0;
-    if (0 == num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    static int sms_of[kMaxDevices] = {0};
+    int dev = 0; cudaGetDevice(&dev);
+    int &num_sms = sms_of[(dev >= 0 && dev < kMaxDevices) ? dev : 0];
+    if (0 == num_sms) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     uint32_t const grid = std::min<uint32_t>(p.nUnits, uint32_t(ctas)*uint32_t(num_sms));
     if (grid > 0) kernel<<<grid, kTcThreads, smem_req, stream>>>(a);
     TFQ_CUDA(cudaGetLastError());

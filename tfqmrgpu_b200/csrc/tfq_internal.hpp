@@ -160,6 +160,22 @@ constexpr int spmm_ti(bool is_double, int LM, int LN) {
 bool block_size_allowed(int lm, int ln);
 extern const int kAllowedBlockSizes[15][2];
 
+// Dynamic shared memory above 48 KiB is opted in per kernel AND per device: remember the largest request per device
+// (one process may drive several GPUs through several handles).
+constexpr int kMaxDevices = 64;
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes, size_t (&configured)[kMaxDevices]) {
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (cudaSuccess != err) return err;
+    if (dev < 0 || dev >= kMaxDevices) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+    if (bytes > configured[dev]) {
+        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+        if (cudaSuccess == err) configured[dev] = bytes;
+    }
+    return err;
+}
+
 template <typename T> inline T* ws(Plan const &p, size_t off) { return reinterpret_cast<T*>(p.pBuffer + off); }
 
 } // namespace tfq
