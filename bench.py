@@ -14,6 +14,9 @@ A "step" is one complete tfQMR solve of that system through the C-ABI of libtfQM
           average launch duration measured with CUDA events on the solver's stream inside the timed steps;
   cpu_baseline : the unmodified reference CPU build (oracle/_ref) - or the oracle port when that is not
           available - on a bounded sample (6^3 block rows, same blocks / RHS / tolerance), N=1 rank 0 only.
+          The same baseline leg also times, when oracle/_ref holds it, the reference's own CUDA kernels (unmodified sources
+          compiled for sm_100) on the full workload on this GPU and reports them as `reference_gpu` - a reported baseline
+          like cpu_baseline, after the timed region, never part of the product path (`--no-cpu` skips both).
 
 N > 1 (torchrun): every rank solves its own 64 right-hand-side columns of a 64*N-column problem with A
 replicated (RHS block-column sharding, no data-path collective); value = all ranks' flops / max time.
