@@ -5,7 +5,7 @@ warm (working set 45 MB < L2) and cold (L2 flushed between launches), GB/s and G
 next to the oracle's restatement of the reference's OpenMP CPU check loop (bench_tfqmrgpu.cu:358-404) on the host cores."""
 import json, os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch
 import orclib as O

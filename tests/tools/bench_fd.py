@@ -4,7 +4,7 @@ column) through the C-ABI: solve time and iterations, next to the reference's ow
 and the reference CPU build.  Launch-latency-bound: the roofline fraction is not meaningful here."""
 import json, os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import orclib as O
 from tfqmrgpu_b200 import api, problems as P
