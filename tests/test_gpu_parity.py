@@ -444,6 +444,29 @@ def _stencil_product(ncol, fill_seed=1):
     return info, Y, Y32, Y64
 
 
+def test_two_devices_in_one_process():
+    """The library follows the caller's current device (like the reference) and opts kernels into large dynamic shared memory
+    per device: the same products and a solve on cuda:0 and cuda:1 from one process give identical results."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = []
+    try:
+        for dev in (0, 1):
+            torch.cuda.set_device(dev)
+            info, Y, _, _ = _stencil_product(2)                                   # tcgen05 product
+            assert info["use_tc"] == 1
+            prob = P.random_system(12, 8, 8, seed=3)                                # small-block product + full solve, fp32
+            r = _solve_case(prob, "c", 1e-4, 200, "n", "n")
+            prob64 = P.random_system(10, 32, 32, seed=4)                            # DMMA product + full solve, fp64
+            r64 = _solve_case(prob64, "z", 1e-9, 200, "n", "n")
+            out.append((Y, r["X"], r["info"]["iterations"], r64["X"], r64["info"]["iterations"]))
+    finally:
+        torch.cuda.set_device(0)
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][3], out[1][3])
+    assert out[0][2] == out[1][2] and out[0][4] == out[1][4]
+
+
 @pytest.mark.parametrize("ncol", [1, 2, 3])
 def test_tensor_core_product_accuracy_statement(ncol):
     """Complex fp32 32x32 blocks run on tcgen05 (3xTF32, separate correction accumulator).  Stated accuracy (DESIGN.md
