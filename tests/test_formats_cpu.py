@@ -148,3 +148,17 @@ def test_reference_readers_accept_our_files(tmp_path):
     assert "# ran 42 iterations" in gold
     assert _ref_bench_log(ours_xml) == gold
     assert _ref_bench_log(ours_txt) == gold
+
+
+def test_multiplication_plan_file_roundtrip(tmp_path, plan_unordered=None):
+    """write_multiplication_plan produces the format of test/multiplication/plan_unordered.14-287-16: reading it back gives the
+    lists, and the golden plan (committed as arrays) survives the trip."""
+    g = np.load(os.path.join(HERE, "golden", "plan_unordered.npz"))
+    starts, pairs = g["starts"], g["pairs"].reshape(-1, 2)
+    nnzA = int(g["nnz"][1])
+    f = str(tmp_path / "plan.txt")
+    F.write_multiplication_plan(f, starts, pairs, nnzA, starts.size - 1)
+    s2, p2, nY, nA, nX, _ = P.read_multiplication_plan(f)
+    assert np.array_equal(s2, starts) and np.array_equal(p2, pairs) and (nY, nA, nX) == (starts.size - 1, nnzA, starts.size - 1)
+    assert open(f).readline() == "#nnzb_for_Y_A_X= 4490 13109 4490 \n"
+

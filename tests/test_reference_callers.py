@@ -72,6 +72,49 @@ def test_reference_bench_reads_files_we_wrote(tmp_path):
     assert vals[1] == vals[0] and vals[2] == vals[0]
 
 
+def _cli(*args):
+    import sys
+    out = subprocess.run([sys.executable, "-m", "tfqmrgpu_b200.bench_cli", *args], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    return out.stdout
+
+
+def test_bench_cli_multiply_on_the_reference_plan(tmp_path):
+    """`bench_tfqmrgpu multiply <plan> f|d reps samples lm ln` conventions and result lines, on this library's
+    product kernels, for the reference's plan_unordered.14-287-16 (written back to its text format from the golden arrays)."""
+    from tfqmrgpu_b200 import formats as F
+    g = np.load(os.path.join(ROOT, "tests", "golden", "plan_unordered.npz"))
+    plan = str(tmp_path / "plan_unordered.14-287-16")
+    F.write_multiplication_plan(plan, g["starts"], g["pairs"], int(g["nnz"][1]), int(g["nnz"][2]))
+    for fF, bar in (("f", 1e-4), ("d", 1e-10)):
+        txt = _cli("multiply", plan, fF, "20", "3", "16", "16")
+        assert "# found 4490 result elements" in txt and "# found 50526 operations" in txt and "Warning" not in txt
+        m = re.search(r"# GPU maxdev ([0-9.e+-]+) avgdev ([0-9.e+-]+)", txt)
+        assert m and float(m.group(1)) <= bar, txt[-1500:]
+        m = re.search(r"# GPU performance \(lm,ln,tune\)=\( 16, 16,0\) is  ([0-9.]+) G[fF]lop/sec", txt)
+        assert m and float(m.group(1)) > 1000., txt[-1500:]
+
+
+@pytest.mark.skipif(not _have("bench_tfqmrgpu_ours"), reason="reference bench not built")
+def test_bench_cli_tfqmr_matches_the_reference_harness(tmp_path):
+    """`tfQMR <file> z`: same `# GPU maxdev ... avgdev ...` line as the reference's harness linked against this library, for the
+    XML file and for the legacy dump of the same problem."""
+    from tfqmrgpu_b200 import formats as F
+    gold = os.path.join(ROOT, "tests", "golden", "FD_problem.xml")
+    legacy = str(tmp_path / "fd_problem.txt")
+    F.write_legacy(legacy, P.read_xml(gold))
+    out = subprocess.run([os.path.join(REFDIR, "bench_tfqmrgpu_ours"), "tfQMR", gold, "z"], capture_output=True, text=True, timeout=300)
+    ref = re.search(r"# GPU maxdev ([0-9.e+-]+) avgdev ([0-9.e+-]+) maxrel ([0-9.e+-]+)", out.stdout)
+    assert ref, out.stdout[-1500:]
+    for f in (gold, legacy):
+        txt = _cli("tfQMR", f, "z", "1", "2000")
+        m = re.search(r"# GPU maxdev ([0-9.e+-]+) avgdev ([0-9.e+-]+) maxrel ([0-9.e+-]+)", txt)
+        assert m and m.groups() == ref.groups(), (m and m.groups(), ref.groups())
+        s = re.search(r"# solve: status (\d+), (\d+) iterations, residual ([0-9.e+-]+)", txt)
+        assert s and int(s.group(1)) == 0 and 40 <= int(s.group(2)) <= 43 and float(s.group(3)) < 1e-9
+        assert "# found tolerance= 1e-09" in txt and "# requested precision= 'z' for LM= 8, LN= 8" in txt
+
+
 CASES = golden_cases()
 
 

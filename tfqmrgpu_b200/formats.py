@@ -272,3 +272,18 @@ def read_legacy(path: str) -> Problem:
     del ncols
     return Problem(Bsr(A["rp"], A["ci"], A["val"]), Bsr(X["rp"], X["ci"], X["val"]), Bsr(B["rp"], B["ci"], B["val"]),
                    A["val"].shape[2], B["val"].shape[2], tol, path, X_exact=None)
+
+
+# ------------------------------------------------------------------------------------------------
+def write_multiplication_plan(path: str, starts: np.ndarray, pairs: np.ndarray, nnzA: int, nnzX: int) -> None:
+    """The plan dump ``bench_tfqmrgpu multiply`` reads (bench_tfqmrgpu.cu:456-498; test/multiplication/plan_*): a header
+    ``#nnzb_for_Y_A_X= nY nA nX`` and one line ``iY iA iX beta`` per pair, beta = 0 on the first pair of a Y block."""
+    starts = np.asarray(starts, np.int64); pairs = np.asarray(pairs, np.int64).reshape(-1, 2)
+    nY = starts.size - 1
+    out = ["#nnzb_for_Y_A_X= %d %d %d \n" % (nY, nnzA, nnzX)]
+    for y in range(nY):
+        for p in range(starts[y], starts[y + 1]):
+            out.append("%d %d %d %d \n" % (y, pairs[p, 0], pairs[p, 1], 0 if p == starts[y] else 1))
+    with open(path, "w") as f:
+        f.write("".join(out))
+
