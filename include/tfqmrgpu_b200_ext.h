@@ -75,6 +75,21 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getSolveStats(tfqmrgpuBsrsvPlan_t plan, double 
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_setProfiling(tfqmrgpuBsrsvPlan_t plan, int on);
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_getSolveProfile(tfqmrgpuBsrsvPlan_t plan, double profile[8]);
 
+/* User-defined linear operator - the C-callable form of the reference's C++ `action_t` concept (README.md "User-defined
+ * linear operators", tfqmrgpu_core.hxx:27-37: the solver only ever calls action.multiply(y, x, ...)).  When `op` is set, every
+ * product Y = A*X of solve() calls it instead of the library's block-sparse product; setMatrix('A') is then not needed.
+ *   y, x   device pointers to X-shaped vectors in the solver's storage: real_t [nnzbX][2 (Re|Im)][LM][LN], blocks in the
+ *          column-sorted storage order (getPlanArray kind 4 maps the caller's X block index to the storage index)
+ *   state, expect   device-resident solver control: when expect >= 0 the product is only wanted while *state == expect
+ *          (speculatively enqueued iterations after convergence, and the residual probe, are skipped that way); kernels of
+ *          the operator SHOULD return at once otherwise - ignoring it is correct but wastes up to one product per iteration
+ *   stream the handle's stream: the call must only enqueue work on it and must not synchronise
+ * Return 0 on success; any other value aborts the solve with that status.  With an operator set the iteration is launched
+ * kernel by kernel (no CUDA graph).  `op` = NULL restores the built-in product.  getInfo's flop count keeps the formula of the
+ * block-sparse product. */
+typedef int32_t (*tfqmrgpuxOperator_t)(void *ctx, void *y, void const *x, int32_t const *state, int32_t expect, cudaStream_t stream);
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setOperator(tfqmrgpuBsrsvPlan_t plan, tfqmrgpuxOperator_t op, void *ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -444,6 +444,69 @@ def _stencil_product(ncol, fill_seed=1):
     return info, Y, Y32, Y64
 
 
+class _DevArray:
+    """torch.as_tensor() view of raw device memory (CUDA array interface)"""
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+@pytest.mark.parametrize("prec", ["z", "c"])
+def test_user_defined_operator_matches_builtin_product(prec):
+    """tfqmrgpux_bsrsv_setOperator (the reference's action_t concept): a solve whose products are computed by a
+    caller-supplied operator - here torch, from the same blocks, on the solver's storage layout - follows the built-in solve."""
+    import torch
+    lm, ln = 8, 8
+    prob = P.random_system(14, lm, ln, seed=21, unsorted=True)
+    tol = 1e-9 if prec == "z" else 1e-4
+    base = _solve_case(prob, prec, tol, 200, "n", "n")
+    dt, ts, tdt = (np.float64, "<f8", torch.float64) if prec == "z" else (np.float32, "<f4", torch.float32)
+    vA = P.interleave(prob.A.val, dt); vB = P.interleave(prob.B.val, dt)
+    h, pl = _open(prob)
+    pl.buffer_size_for(lm, ln, prec); pl.set_buffer()
+    lists = pl.plan_lists()
+    perm = torch.as_tensor(lists["perm"].astype(np.int64), device="cuda")
+    pairs = lists["pairs"].reshape(-1, 2).astype(np.int64)
+    ydst = np.repeat(np.arange(pl.nnzbX), np.diff(lists["starts"].astype(np.int64)))
+    iA = torch.as_tensor(pairs[:, 0], device="cuda")
+    sx = perm[torch.as_tensor(pairs[:, 1], device="cuda")]            # storage index of every pair's X block
+    sy = perm[torch.as_tensor(ydst, device="cuda")]                    # storage index of every pair's Y block
+    Ac = torch.as_tensor(prob.A.val.astype(np.complex128 if prec == "z" else np.complex64), device="cuda")   # [nnzbA][i][k], 'n'
+    shape = (pl.nnzbX, 2, lm, ln)
+    calls = []
+
+    def op(y_ptr, x_ptr, state_ptr, expect, stream):
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+            x = torch.as_tensor(_DevArray(x_ptr, shape, ts), device="cuda")
+            y = torch.as_tensor(_DevArray(y_ptr, shape, ts), device="cuda")
+            xc = torch.complex(x[:, 0], x[:, 1])
+            prod = torch.matmul(Ac[iA], xc[sx])
+            yc = torch.zeros_like(xc).index_add_(0, sy, prod)
+            y[:, 0] = yc.real; y[:, 1] = yc.imag
+        calls.append(expect)
+        return 0
+    pl.set_operator(op)
+    pl.set_matrix("B", vB, "n")                                        # no setMatrix('A'): the operator replaces it
+    st = pl.solve(tol, 200)
+    info = pl.info()
+    X = pl.get_matrix("X", "n", L.LAYOUT_RRRRIIII).reshape(pl.nnzbX, 2, lm, ln)
+    assert st == 0 and len(calls) >= 2*info["iterations"]
+    assert abs(info["iterations"] - base["info"]["iterations"]) <= 1
+    scale = np.abs(base["X"]).max()
+    assert np.abs(X - base["X"]).max() <= (10 if prec == "z" else 50)*tol*scale
+    # back to the built-in product on the same plan
+    pl.set_operator(None)
+    pl.set_matrix("A", vA, "n")
+    assert pl.solve(tol, 200) == 0 and pl.info()["iterations"] == base["info"]["iterations"]
+    X2 = pl.get_matrix("X", "n", L.LAYOUT_RRRRIIII).reshape(pl.nnzbX, 2, lm, ln)
+    assert np.array_equal(X2, base["X"])
+    # an operator that fails aborts the solve with its status
+    pl.set_operator(lambda *a: 14)
+    with pytest.raises(api.TfqmrError) as err:
+        pl.solve(tol, 200)
+    assert "status 14" in str(err.value)
+    pl.close(); h.close()
+
+
 def test_two_devices_in_one_process():
     """The library follows the caller's current device (like the reference) and opts kernels into large dynamic shared memory
     per device: the same products and a solve on cuda:0 and cuda:1 from one process give identical results."""

@@ -33,7 +33,7 @@ EXT_SYMBOLS = [
     "tfqmrgpux_getVersion", "tfqmrgpux_setVerbosity", "tfqmrgpux_bsrsv_getPlanArray", "tfqmrgpux_bsrsv_getPlanInfo",
     "tfqmrgpux_bsrsv_setV3", "tfqmrgpux_bsrsv_getV3", "tfqmrgpux_bsrsv_multiply", "tfqmrgpux_bsrsv_getVector",
     "tfqmrgpux_bsrsv_getWindow", "tfqmrgpux_bsrsv_getRhsStatus", "tfqmrgpux_bsrsv_getSolveStats", "tfqmrgpux_randomShadow",
-    "tfqmrgpux_bsrsv_setProfiling", "tfqmrgpux_bsrsv_getSolveProfile",
+    "tfqmrgpux_bsrsv_setProfiling", "tfqmrgpux_bsrsv_getSolveProfile", "tfqmrgpux_bsrsv_setOperator",
 ]
 FORTRAN_SYMBOLS = [
     "tfqmrgpuprinterror_", "tfqmrgpucreatehandle_", "tfqmrgpudestroyhandle_", "tfqmrgpusetstream_",
@@ -117,6 +117,7 @@ def load():
     lib.tfqmrgpux_randomShadow.restype = st; lib.tfqmrgpux_randomShadow.argtypes = [vp, vp, C.c_size_t]
     lib.tfqmrgpux_bsrsv_setProfiling.restype = st; lib.tfqmrgpux_bsrsv_setProfiling.argtypes = [vp, C.c_int]
     lib.tfqmrgpux_bsrsv_getSolveProfile.restype = st; lib.tfqmrgpux_bsrsv_getSolveProfile.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.tfqmrgpux_bsrsv_setOperator.restype = st; lib.tfqmrgpux_bsrsv_setOperator.argtypes = [vp, vp, vp]
     _lib = lib
     return lib
 

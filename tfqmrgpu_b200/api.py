@@ -158,6 +158,28 @@ class BsrsvPlan:
         return dict(starts=self.plan_array(0), pairs=self.plan_array(1), subset=self.plan_array(2),
                     colindx=self.plan_array(3), perm=self.plan_array(4), colstart=self.plan_array(5))
 
+    def set_operator(self, fn):
+        """User-defined operator (tfqmrgpux_bsrsv_setOperator): ``fn(y_ptr, x_ptr, state_ptr, expect, stream) -> int`` is called
+        for every product Y = A*X of solve() with device pointers to X-shaped vectors in storage order
+        ``[nnzbX][2][LM][LN]`` (``plan_lists()['perm']`` maps caller block index -> storage index); ``None`` restores the
+        built-in block-sparse product."""
+        proto = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p)
+        if fn is None:
+            self._op_keepalive = None
+            _check(self.lib.tfqmrgpux_bsrsv_setOperator(self.plan, None, None), "setOperator")
+            return
+
+        def trampoline(_ctx, y, x, state, expect, stream):
+            try:
+                return int(fn(int(y or 0), int(x or 0), int(state or 0), int(expect), int(stream or 0)) or 0)
+            except Exception:          # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return L.UNDOCUMENTED_ERROR
+        cb = proto(trampoline)
+        self._op_keepalive = cb
+        _check(self.lib.tfqmrgpux_bsrsv_setOperator(self.plan, C.cast(cb, C.c_void_p), None), "setOperator")
+
     def plan_info(self) -> dict:
         info = (C.c_int64*16)()
         _check(self.lib.tfqmrgpux_bsrsv_getPlanInfo(self.plan, info), "getPlanInfo")

@@ -487,6 +487,14 @@ tfqmrgpuStatus_t tfqmrgpux_randomShadow(tfqmrgpuHandle_t handle, float *devOut, 
     return st;
 }
 
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setOperator(tfqmrgpuBsrsvPlan_t plan, tfqmrgpuxOperator_t op, void *ctx) {
+    if (nullptr == plan) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan &p = *P(plan);
+    p.user_op = op; p.user_ctx = op ? ctx : nullptr;
+    plan_drop_graph(p);          // a captured iteration body holds the built-in product
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_multiply(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, int nrep) {
     if (nullptr == plan || nullptr == handle) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     Plan &p = *P(plan);

@@ -103,7 +103,7 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
     }
     auto mark = [&](int which) { return p.profile ? cudaEventRecord(p.prof_ev[which], stream) : cudaSuccess; };
     TFQ_CUDA(mark(0));
-    bool const use_graph = graphs_enabled() && !p.profile && maxIterations > 0;
+    bool const use_graph = graphs_enabled() && !p.profile && maxIterations > 0 && nullptr == p.user_op;   // (a callback cannot be captured blindly)
     if (use_graph && nullptr == p.body_exec) {
         tfqmrgpuStatus_t const gst = build_body_graph(p);
         if (TFQMRGPU_STATUS_SUCCESS != gst) return gst;

@@ -485,6 +485,10 @@ tfqmrgpuStatus_t launch_sized(Plan const &p, void *y, void const *x, int expect,
 
 tfqmrgpuStatus_t launch_spmm(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream)
 {
+    if (p.user_op) {             // tfqmrgpux_bsrsv_setOperator: the caller's Y = A*X
+        int32_t const st = p.user_op(p.user_ctx, y, x, reinterpret_cast<int32_t const*>(&ws<Control const>(p, p.off_ctl)->state), expect, stream);
+        return st ? tfqmrgpuStatus_t(st) : TFQMRGPU_STATUS_SUCCESS;
+    }
     if (p.use_tc) return launch_spmm_tc(p, y, x, expect, stream);
     if (p.use_dmma) return launch_spmm_dmma(p, y, x, expect, stream);
     switch (p.LM*1000 + p.LN) {

@@ -77,6 +77,8 @@ struct Plan {
     uint32_t nUnits = 0, gmax = 1; uint64_t nEntries = 0;
     bool use_tc = false;              // block-sparse product on the tensor cores (spmm_tc.cu)
     bool use_dmma = false;            // complex fp64 product on the FP64 tensor pipe (spmm_dmma.cu)
+    tfqmrgpuxOperator_t user_op = nullptr;   // user-defined operator instead of the block-sparse product (ext header)
+    void *user_ctx = nullptr;
     bool use_small = false;           // LM <= 8: register-staged batches of entries instead of the bulk-copy ring (spmm.cu)
     uint32_t *d_unit_e0 = nullptr;    // [nUnits+1] first entry of every unit
     uint32_t *d_unit_y = nullptr;     // [nUnits*gmax] storage index of the unit's Y blocks (kNoBlock = none)
