@@ -190,6 +190,25 @@ def test_small_block_switch(monkeypatch):
     pl.close(); h.close()
 
 
+@pytest.mark.parametrize("lmln,prec", [((4, 4), "c"), ((8, 8), "z"), ((16, 16), "c"), ((32, 32), "z"), ((32, 32), "c")],
+                         ids=["4x4c", "8x8z", "16x16c", "32x32z", "32x32c"])
+def test_product_with_duplicate_entries_and_empty_rows(lmln, prec):
+    """Degenerate patterns the reference's createPlan accepts: a block column listed twice in a row of A (both blocks are added),
+    rows of A without blocks, rows of X without blocks, a Y block without any pair (it must come out as zero), unsorted columns.
+    Plan lists bit-exact against the oracle's restatement of createPlan, product against its multiply - for every product kernel."""
+    lm, ln = lmln
+    rpA = np.array([0, 3, 3, 5, 6, 8], np.int32); ciA = np.array([1, 1, 3,   2, 0,   4,   3, 0], np.int32)
+    rpX = np.array([0, 2, 3, 5, 5, 6], np.int32); ciX = np.array([1, 0,   0,   2, 0,   1], np.int32)
+    A, X, Y, lists = _spmm_case(5, rpA, ciA, rpX, ciX, lm, ln, prec)
+    op = O.OraclePlan(5, rpA, ciA, rpX, ciX, rpX, ciX)
+    assert np.array_equal(lists["starts"], op.starts) and np.array_equal(lists["pairs"].reshape(-1), np.asarray(op.pairs).reshape(-1))
+    npairs = np.diff(lists["starts"].astype(np.int64))
+    assert npairs.min() == 0 and npairs.max() >= 2            # a Y block without pairs, and the duplicated column counted twice
+    Yo = O.multiply(A, X, lists["starts"], lists["pairs"], lm, ln)
+    assert np.abs(Y - Yo).max() <= (2e-4 if prec == "c" else 1e-11)
+    assert not np.any(Y[npairs == 0])
+
+
 # ---- full solves ------------------------------------------------------------------------------------------
 def _solve_case(prob, prec, tol, maxit, tA, tB, v3=None, index_offset=0):
     dt = np.float64 if prec == "z" else np.float32
