@@ -209,6 +209,23 @@ def test_product_with_duplicate_entries_and_empty_rows(lmln, prec):
     assert not np.any(Y[npairs == 0])
 
 
+@pytest.mark.parametrize("lm,ln", [(16, 16), (32, 32), (32, 64)], ids=["16x16", "32x32", "32x64"])
+def test_tensor_core_product_long_rows_use_accumulation_passes(lm, ln):
+    """Rows with more entries than one accumulation pass holds (kChain = 896/LM entries in spmm_tc.cu): a later pass adds to the
+    Y of the earlier ones.  64 entries per row; error bound relative to the sum of the magnitudes of the terms."""
+    prob = P.random_system(64, lm, ln, ncols=3, pA=1.0, pX=1.0, seed=lm + ln, unsorted=True)
+    A, X, Y, lists = _spmm_case(prob.mb, prob.A.rowptr, prob.A.colind, prob.X.rowptr, prob.X.colind, lm, ln, "c")
+    assert np.diff(lists["starts"].astype(np.int64)).max() > 896//lm
+    Y64 = O.multiply(A.astype(np.float64), X.astype(np.float64), lists["starts"], lists["pairs"], lm, ln, nthreads=8)
+    # sum of |terms| per output element: (|Re| + |Im|) of A times (|Re| + |Im|) of X as a real product.  The cos/sin fill makes
+    # sums that cancel 100-fold (max|Y| ~ 3 from ~1000 of |terms|), the case where the once-per-MMA truncation of the accumulator
+    # shows most: measured 1.8e-7 * sum|terms| at 32x32 (fp32 FMA order: 1e-8), 2e-8 at 32x64 and 16x16
+    Aabs = np.zeros_like(A, dtype=np.float64); Aabs[:, 0] = np.abs(A[:, 0]) + np.abs(A[:, 1])
+    Xabs = np.zeros_like(X, dtype=np.float64); Xabs[:, 0] = np.abs(X[:, 0]) + np.abs(X[:, 1])
+    terms = O.multiply(Aabs, Xabs, lists["starts"], lists["pairs"], lm, ln, nthreads=8)[:, 0].max()
+    assert np.abs(Y - Y64).max() <= 4e-7*terms
+
+
 # ---- full solves ------------------------------------------------------------------------------------------
 def _solve_case(prob, prec, tol, maxit, tA, tB, v3=None, index_offset=0):
     dt = np.float64 if prec == "z" else np.float32
