@@ -28,6 +28,7 @@
 // of entry e+1 are in flight while entry e is split, and two CTAs per SM overlap each other's
 // prologue/epilogue.
 #include "tfq_internal.hpp"
+#include <cstdlib>
 #include <algorithm>
 
 namespace tfq {
@@ -44,6 +45,7 @@ struct TcArgs {
     float *y; float const *x; float const *A;
     uint32_t const *unit_e0, *unit_y, *ent_a, *ent_x;
     Control const *ctl; int expect; int gstride; uint32_t nUnits;
+    int chain;        // entries per accumulation pass
 };
 
 __device__ __forceinline__ uint32_t smem_u32(void const *p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -195,7 +197,7 @@ spmm_tc_kernel(TcArgs const a)
     constexpr int kRingA = TcShape<LM>::ring;
     constexpr uint32_t kTmemCols = TcShape<LM>::tmem_cols, kTmemStage0 = TcShape<LM>::acc_cols, kStageCols = TcShape<LM>::stage_cols;
     constexpr int KH = LM/2;              // k values per converter thread (two warps share a lane quarter)
-    constexpr int kChain = (64 == LM) ? 7 : 896/LM;   // entries per accumulation pass: LM/8 MMA steps each; 112 steps per pass (56 at LM = 64)
+    int const kChain = a.chain;           // entries per accumulation pass: LM/8 MMA steps each; default 112 steps per pass (56 at LM = 64)
     constexpr int G  = 64/LN;             // block columns per unit
     constexpr int N  = 2*LM;              // MMA N: (Re|Im of A, i)
     constexpr int KS = LM/8;              // k-steps of 8 (TF32) per entry
@@ -482,6 +484,10 @@ tfqmrgpuStatus_t launch_tc(Plan const &p, void *y, void const *x, int expect, cu
     a.y = static_cast<float*>(y); a.x = static_cast<float const*>(x); a.A = ws<float const>(p, p.off_A);
     a.unit_e0 = p.d_unit_e0; a.unit_y = p.d_unit_y; a.ent_a = p.d_ent_a; a.ent_x = p.d_ent_x;
     a.ctl = ws<Control const>(p, p.off_ctl); a.expect = expect; a.gstride = int(p.gmax); a.nUnits = p.nUnits;
+    // TFQMRGPU_TC_CHAIN = entries per accumulation pass (default 896/LM, 7 at LM = 64): shorter chains cut the truncation error of
+    // strongly cancelling sums (the accumulator is truncated once per MMA) for one more epilogue per pass
+    static int const chain_env = [] { char const *e = std::getenv("TFQMRGPU_TC_CHAIN"); return e ? std::atoi(e) : 0; }();
+    a.chain = (chain_env > 0) ? chain_env : ((64 == LM) ? 7 : 896/LM);
     static int sms_of[kMaxDevices] = {0};
     int dev = 0; cudaGetDevice(&dev);
     int &num_sms = sms_of[(dev >= 0 && dev < kMaxDevices) ? dev : 0];
