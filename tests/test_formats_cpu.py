@@ -150,6 +150,19 @@ def test_reference_readers_accept_our_files(tmp_path):
     assert _ref_bench_log(ours_txt) == gold
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "bench_tfqmrgpu_cpu")), reason="oracle/_ref/bench_tfqmrgpu_cpu not built")
+def test_reference_readers_agree_on_a_complex_problem(tmp_path):
+    """A complex-valued system (the FD file is real): our XML (type complex64, 17 digits) and our legacy dump of the same problem
+    run to the same iteration log through the reference's two readers."""
+    p = P.random_system(9, 4, 4, ncols=5, seed=11)
+    xml, txt = str(tmp_path / "cplx.xml"), str(tmp_path / "cplx_problem.txt")
+    F.write_xml(xml, F.xml_from_problem(p, tolerance=1e-8), lossless=True)
+    F.write_legacy(txt, p, tolerance=1e-8)
+    assert F.read_xml_raw(xml).op("A").is_complex
+    a, b = _ref_bench_log(xml), _ref_bench_log(txt)
+    assert a == b and any(ln.startswith("# ran ") for ln in a)
+
+
 def test_multiplication_plan_file_roundtrip(tmp_path, plan_unordered=None):
     """write_multiplication_plan produces the format of test/multiplication/plan_unordered.14-287-16: reading it back gives the
     lists, and the golden plan (committed as arrays) survives the trip."""
