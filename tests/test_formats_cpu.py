@@ -175,3 +175,20 @@ def test_multiplication_plan_file_roundtrip(tmp_path, plan_unordered=None):
     assert np.array_equal(s2, starts) and np.array_equal(p2, pairs) and (nY, nA, nX) == (starts.size - 1, nnzA, starts.size - 1)
     assert open(f).readline() == "#nnzb_for_Y_A_X= 4490 13109 4490 \n"
 
+
+
+def test_bench_cli_fill_and_checker_match_the_oracle():
+    """bench_cli's cos/sin fill and its numpy check of Y = A*X (the CLI's stand-in for the harness's CPU check loop,
+    bench_tfqmrgpu.cu:277-285 and :366-392) against the oracle's restatement of both."""
+    import orclib as O
+    from tfqmrgpu_b200 import bench_cli as B
+    for lm, ln, dt in ((4, 5, np.float32), (8, 8, np.float64)):
+        assert np.array_equal(B.fill_cos_sin(7, lm, ln, dt), O.fill_cos_sin(7, lm, ln, dt))
+    g = np.load(os.path.join(HERE, "golden", "plan_unordered.npz"))
+    starts, pairs = g["starts"][:201], g["pairs"].reshape(-1, 2)
+    pairs = pairs[:starts[-1]]
+    nA, nX = int(pairs[:, 0].max()) + 1, int(pairs[:, 1].max()) + 1
+    A = B.fill_cos_sin(nA, 16, 16, np.float64); X = B.fill_cos_sin(nX, 16, 16, np.float64)
+    Y = B._pairs_product(A, X, starts, pairs)
+    Yo = O.multiply(A, X, starts, pairs, 16, 16)[:200]
+    assert np.abs(np.stack([Y.real, Y.imag], axis=1) - Yo).max() <= 1e-12
