@@ -261,31 +261,41 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_setMatrix(tfqmrgpuHandle_t handle, tfqmrgpuBsrsv
         char *const dst = p.pBuffer + p.off_A;
         size_t const blockBytes = 2*size_t(p.LM)*p.LM*s, bytes = size_t(nnzb)*blockBytes;
         size_t const chunkBytes = size_t(256) << 20;
+        // after the layout conversion of a chunk: block maxima for the row scales of the fp16-pair operand (xop.cu)
+        auto converted = [&](uint32_t b0, uint32_t nb) -> tfqmrgpuStatus_t {
+            tfqmrgpuStatus_t const cst = convert_inplace(p, dst + size_t(b0)*blockBytes, nb, p.LM, p.LM, is_double, layout, trans, scal_imag, stream, p.use_tc);
+            if (cst || !p.use_tc16) return cst;
+            return launch_aop_blockmax(p, b0, nb, stream);
+        };
         if (bytes <= chunkBytes) {
             TFQ_CUDA(cudaMemcpyAsync(dst, val, bytes, cudaMemcpyHostToDevice, stream));
-            return convert_inplace(p, dst, nnzb, p.LM, p.LM, is_double, layout, trans, scal_imag, stream, p.use_tc);
+            tfqmrgpuStatus_t const cst = converted(0, nnzb);
+            if (cst || !p.use_tc16) return cst;
+            return launch_aop_convert(p, stream);
         }
         // large operator: upload in chunks on a copy stream while the layout kernel converts the previous chunk on the
         // caller's stream (the conversion then hides completely behind the PCIe transfer)
         if (nullptr == p.copy_stream) TFQ_CUDA(cudaStreamCreateWithFlags(&p.copy_stream, cudaStreamNonBlocking));
-        cudaEvent_t ev;
-        TFQ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        TFQ_CUDA(cudaEventRecord(ev, stream));                   // earlier work on the caller's stream may still read A
-        TFQ_CUDA(cudaStreamWaitEvent(p.copy_stream, ev, 0));
-        TFQ_CUDA(cudaEventDestroy(ev));
+        if (nullptr == p.chunk_ev[0]) {
+            for (auto &e : p.chunk_ev) TFQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        TFQ_CUDA(cudaEventRecord(p.chunk_ev[0], stream));        // earlier work on the caller's stream may still read A
+        TFQ_CUDA(cudaStreamWaitEvent(p.copy_stream, p.chunk_ev[0], 0));
         uint32_t const blocksPerChunk = uint32_t(chunkBytes/blockBytes);
         tfqmrgpuStatus_t cst = TFQMRGPU_STATUS_SUCCESS;
-        for (uint32_t b0 = 0; b0 < nnzb && TFQMRGPU_STATUS_SUCCESS == cst; b0 += blocksPerChunk) {
+        int turn = 0;
+        for (uint32_t b0 = 0; b0 < nnzb && TFQMRGPU_STATUS_SUCCESS == cst; b0 += blocksPerChunk, ++turn) {
             uint32_t const nb = std::min(blocksPerChunk, nnzb - b0);
             size_t const off = size_t(b0)*blockBytes;
             TFQ_CUDA(cudaMemcpyAsync(dst + off, static_cast<char const*>(val) + off, size_t(nb)*blockBytes, cudaMemcpyHostToDevice, p.copy_stream));
-            TFQ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            // (re-recording an event that a stream still waits for is fine: the wait took the earlier record)
+            cudaEvent_t const ev = p.chunk_ev[1 + (turn & 1)];
             TFQ_CUDA(cudaEventRecord(ev, p.copy_stream));
             TFQ_CUDA(cudaStreamWaitEvent(stream, ev, 0));
-            TFQ_CUDA(cudaEventDestroy(ev));                      // released once the event has completed
-            cst = convert_inplace(p, dst + off, nb, p.LM, p.LM, is_double, layout, trans, scal_imag, stream, p.use_tc);
+            cst = converted(b0, nb);
         }
-        return cst;
+        if (cst || !p.use_tc16) return cst;
+        return launch_aop_convert(p, stream);
     }
     if ('b' == v) {
         char *const dst = p.pBuffer + p.off_B;
@@ -441,7 +451,7 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getPlanInfo(tfqmrgpuBsrsvPlan_t plan, int64_t i
     if (nullptr == plan || nullptr == info) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     Plan const &p = *P(plan);
     int64_t const v[16] = {p.nnzbX, p.nnzbB, p.nnzbA, int64_t(p.nCols), int64_t(p.nPairs), p.LM, p.LN, p.precision,
-                           int64_t(p.nTiles), int64_t(p.nUnits), int64_t(p.gmax), int64_t(p.nEntries), p.mb, int64_t(p.use_tc), int64_t(p.use_dmma), int64_t(p.use_small)};
+                           int64_t(p.nTiles), int64_t(p.nUnits), int64_t(p.gmax), int64_t(p.nEntries), p.mb, int64_t(p.use_tc || p.use_tc16), int64_t(p.use_dmma), int64_t(p.use_small)};
     std::memcpy(info, v, sizeof(v));
     return TFQMRGPU_STATUS_SUCCESS;
 }
@@ -527,7 +537,7 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getWindow(tfqmrgpuBsrsvPlan_t plan, char var, s
         case 'x': *offset = p.off_v[1]; *length = p.vecBytes; break;
         case 'y': *offset = p.off_v[9]; *length = p.vecBytes; break;
         case '3': *offset = p.off_v[3]; *length = size_t(p.nnzbX)*2*p.LM*p.LN*4; break;
-        case 'a': *offset = p.off_A; *length = size_t(p.nnzbA)*2*p.LM*p.LM*s; break;
+        case 'a': *offset = p.off_A; *length = size_t(p.nnzbA)*2*p.LM*p.LM*s + (p.use_tc16 ? size_t(p.mb)*4 : 0); break; // (+ row scales)
         case 'b': *offset = p.off_B; *length = size_t(p.nnzbB)*2*p.LM*p.LN*s; break;
         default: return TFQ_ERRC(TFQMRGPU_VARIABLENAME_UNKNOWN, var);
     }

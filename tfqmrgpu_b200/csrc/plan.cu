@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <queue>
+#include <functional>
 
 namespace tfq {
 
@@ -110,6 +112,39 @@ __global__ void k_invert(int n, uint32_t const *__restrict__ iperm, uint32_t *__
 __global__ void k_bpos(int nnzbB, uint32_t const *__restrict__ subset, uint32_t const *__restrict__ perm, uint32_t *__restrict__ bpos) {
     int const ib = blockIdx.x*blockDim.x + threadIdx.x;
     if (ib < nnzbB) bpos[ib] = perm[subset[ib]];
+}
+
+__global__ void k_blockcol(int n, uint32_t const *__restrict__ iperm, uint16_t const *__restrict__ colindx, uint32_t *__restrict__ blockcol) {
+    int const s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s < n) blockcol[s] = colindx[iperm[s]];
+}
+
+// 64 x 64 blocks on the 32 x 32 tensor-core kernel (spmm_tc16.cu): every unit (one Y block) becomes two units (row halves
+// ih) whose two block columns are the column halves jh of that Y block; every entry becomes two (k halves kh).
+// Sub-block numbering: A (ia, ih, kh), X (ix, kh, jh), Y (iy, ih).
+__global__ void k_expand_v64(uint32_t nUnits, uint32_t const *__restrict__ e0, uint32_t const *__restrict__ unit_y,
+                             uint32_t const *__restrict__ unit_row, uint32_t const *__restrict__ ent_a, uint32_t const *__restrict__ ent_x,
+                             uint32_t *__restrict__ e0v, uint32_t *__restrict__ unit_yv, uint32_t *__restrict__ unit_rowv,
+                             uint32_t *__restrict__ ent_av, uint32_t *__restrict__ ent_xv) {
+    uint32_t const u = blockIdx.x*blockDim.x + threadIdx.x;
+    if (u > nUnits) return;
+    if (u == nUnits) { e0v[2*u] = 4*e0[u]; return; }
+    uint32_t const b = e0[u], n = e0[u + 1] - b, iy = unit_y[u];
+    for (uint32_t ih = 0; ih < 2; ++ih) {
+        uint32_t const uv = 2*u + ih, bv = 4*b + ih*2*n;
+        e0v[uv] = bv;
+        unit_rowv[uv] = unit_row[u];
+        unit_yv[2*uv] = unit_yv[2*uv + 1] = (kNoBlock == iy) ? kNoBlock : (2*iy + ih);
+        for (uint32_t t = 0; t < n; ++t) {
+            uint32_t const ia = ent_a[b + t], ix = ent_x[b + t];
+            for (uint32_t kh = 0; kh < 2; ++kh) {
+                uint32_t const ev = bv + 2*t + kh;
+                ent_av[ev] = (2*ia + ih)*2 + kh;
+                ent_xv[2*ev] = (kNoBlock == ix) ? kNoBlock : ((2*ix + kh)*2 + 0);
+                ent_xv[2*ev + 1] = (kNoBlock == ix) ? kNoBlock : ((2*ix + kh)*2 + 1);
+            }
+        }
+    }
 }
 
 // SpMM units: merge the (ascending) pair lists of the unit's Y blocks into one entry list
@@ -298,6 +333,15 @@ tfqmrgpuStatus_t plan_analyse(Plan &p, cudaStream_t stream,
     }
     TFQ_CUDA(cudaMalloc((void**)&p.d_bpos, std::max(nnzbB, 1)*sizeof(uint32_t)));
     if (nnzbB > 0) k_bpos<<<nblk(nnzbB), 256, 0, stream>>>(nnzbB, p.d_subset, p.d_perm, p.d_bpos);
+    TFQ_CUDA(cudaMalloc((void**)&p.d_blockcol, size_t(nnzbX)*sizeof(uint32_t)));
+    k_blockcol<<<nblk(nnzbX), 256, 0, stream>>>(nnzbX, p.d_iperm, p.d_colindx, p.d_blockcol);
+    {
+        std::vector<int32_t> rp0(size_t(mb) + 1);
+        for (int r = 0; r <= mb; ++r) rp0[r] = rpA[r] - off;
+        TFQ_CUDA(cudaMalloc((void**)&p.d_rowptrA, rp0.size()*sizeof(int32_t)));
+        TFQ_CUDA(cudaMemcpyAsync(p.d_rowptrA, rp0.data(), rp0.size()*sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+        TFQ_CUDA(cudaStreamSynchronize(stream));     // rp0 is a local
+    }
     TFQ_CUDA(cudaStreamSynchronize(stream));
     TFQ_CUDA(cudaGetLastError());
     return TFQMRGPU_STATUS_SUCCESS;
@@ -316,17 +360,20 @@ static void free_configured(Plan &p) {
     cudaFree(p.d_unit_y); p.d_unit_y = nullptr;
     cudaFree(p.d_ent_a); p.d_ent_a = nullptr;
     cudaFree(p.d_ent_x); p.d_ent_x = nullptr;
+    cudaFree(p.d_cta_u0); p.d_cta_u0 = nullptr;
+    cudaFree(p.d_unit_row); p.d_unit_row = nullptr;
 }
 
 void plan_release(Plan &p) {
     free_configured(p);
     cudaFree(p.d_starts); cudaFree(p.d_pairs); cudaFree(p.d_subset); cudaFree(p.d_colindx);
-    cudaFree(p.d_perm); cudaFree(p.d_iperm); cudaFree(p.d_bpos);
+    cudaFree(p.d_perm); cudaFree(p.d_iperm); cudaFree(p.d_bpos); cudaFree(p.d_blockcol); cudaFree(p.d_rowptrA);
     if (p.h_ctl) cudaFreeHost(p.h_ctl);
     for (auto &e : p.ev) if (e) cudaEventDestroy(e);
     for (auto &e : p.prof_ev) if (e) cudaEventDestroy(e);
     if (p.capture_stream) cudaStreamDestroy(p.capture_stream);
     if (p.copy_stream) cudaStreamDestroy(p.copy_stream);
+    for (auto &e : p.chunk_ev) if (e) cudaEventDestroy(e);
 }
 
 tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, char precision)
@@ -392,21 +439,24 @@ tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, ch
         g = std::min(g, p.maxColsPerRow);
         // keep one pipeline stage (A block + g X blocks, possibly k-chunked) reasonable: <= 48 KiB at 4 k-rows
         while (g > 1 && 2*4*(size_t(LM) + size_t(g)*LN)*s > 48*1024) --g;
+        // TFQMRGPU_TENSOR: 0 SIMT kernels only, 1 (default) fp16-pair tcgen05 product / DMMA, 2 the earlier 3xTF32 tcgen05 product
         char const *env = std::getenv("TFQMRGPU_TENSOR");
         int const level = env ? std::atoi(env) : 1;
-        p.use_tc = spmm_tc_supported(LM, LN, precision, level);
+        p.use_tc16 = spmm_tc16_supported(LM, LN, precision, level);
+        p.use_tc = !p.use_tc16 && spmm_tc_supported(LM, LN, precision, (level >= 2) ? 1 : 0);
         if (p.use_tc) g = spmm_tc_columns_per_unit(LN);   // 128 MMA rows = g * 2 * LN
+        if (p.use_tc16) g = spmm_tc16_columns_per_unit(LM, LN);
         p.use_dmma = spmm_dmma_supported(LM, LN, precision) && (level >= 1);
         if (p.use_dmma) g = std::min(spmm_dmma_columns_per_unit(LM, LN), std::max(1, p.maxColsPerRow));
         p.gmax = uint32_t(g);
-        std::vector<uint32_t> first, ng;
+        std::vector<uint32_t> first, ng, urow;
         for (int r = 0; r < p.mb; ++r) {
             uint32_t const y0 = p.h_rowptrX[r], n = p.h_rowptrX[r + 1] - p.h_rowptrX[r];
             if (0 == n) continue;
             uint32_t const nu = (n + g - 1)/g;
             for (uint32_t u = 0; u < nu; ++u) {
                 uint32_t const a = uint32_t((uint64_t(n)*u)/nu), b = uint32_t((uint64_t(n)*(u + 1))/nu);
-                first.push_back(y0 + a); ng.push_back(b - a);
+                first.push_back(y0 + a); ng.push_back(b - a); urow.push_back(uint32_t(r));
             }
         }
         p.nUnits = uint32_t(first.size());
@@ -419,7 +469,52 @@ tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, ch
         TFQ_CUDA(cudaMalloc((void**)&p.d_unit_y, std::max<size_t>(first.size()*g, 1)*4));
         k_units<false><<<nblk(p.nUnits, 128), 128, 0, stream>>>(p.nUnits, g, d_first.ptr, d_ng.ptr, p.d_starts, p.d_pairs, p.d_perm,
                                                                  d_cnt.ptr, nullptr, nullptr, nullptr, nullptr);
-        TFQ_CUDA(exclusive_scan(p.d_unit_e0, d_cnt.ptr, first.size() + 1, stream));
+        if (p.use_tc16) {
+            // The persistent kernel runs one CTA per SM.  Deal the units, in block-row order, to the CTA with the fewest entries
+            // so far (equal rows: plain round robin, so the CTAs work on neighbouring rows at any time and the X blocks they share
+            // stay in L2; ragged rows: balanced entry counts), and store every CTA's units - and thereby its entries -
+            // contiguously: the copy warp and the converter warps then stream over ONE flat entry range.
+            std::vector<uint32_t> cnt(first.size() + 1, 0);
+            TFQ_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt.ptr, first.size()*4, cudaMemcpyDeviceToHost, stream));
+            TFQ_CUDA(cudaStreamSynchronize(stream));
+            uint32_t const grid = std::max<uint32_t>(1, std::min<uint32_t>(uint32_t(nsm), p.nUnits));
+            std::vector<std::vector<uint32_t>> mine(grid);
+            {
+                using Load = std::pair<uint64_t, uint32_t>;     // (entries so far, CTA)
+                std::priority_queue<Load, std::vector<Load>, std::greater<Load>> q;
+                for (uint32_t c = 0; c < grid; ++c) q.push({0, c});
+                for (uint32_t u = 0; u < p.nUnits; ++u) {
+                    Load l = q.top(); q.pop();
+                    mine[l.second].push_back(u);
+                    l.first += cnt[u] + 1;                      // (+1: a unit without entries still costs an epilogue)
+                    q.push(l);
+                }
+            }
+            std::vector<uint32_t> first2, ng2, urow2, e02(1, 0), cta_u0(1, 0);
+            first2.reserve(first.size()); ng2.reserve(first.size()); urow2.reserve(first.size());
+            for (uint32_t c = 0; c < grid; ++c) {
+                for (uint32_t u : mine[c]) {
+                    first2.push_back(first[u]); ng2.push_back(ng[u]); urow2.push_back(urow[u]);
+                    e02.push_back(e02.back() + cnt[u]);
+                }
+                cta_u0.push_back(uint32_t(first2.size()));
+            }
+            first.swap(first2); ng.swap(ng2); urow.swap(urow2);
+            p.tc_grid = grid;
+            TFQ_CUDA(cudaMemcpyAsync(d_first.ptr, first.data(), first.size()*4, cudaMemcpyHostToDevice, stream));
+            TFQ_CUDA(cudaMemcpyAsync(d_ng.ptr, ng.data(), ng.size()*4, cudaMemcpyHostToDevice, stream));
+            TFQ_CUDA(cudaMemcpyAsync(p.d_unit_e0, e02.data(), e02.size()*4, cudaMemcpyHostToDevice, stream));
+            TFQ_CUDA(cudaMalloc((void**)&p.d_cta_u0, cta_u0.size()*4));
+            TFQ_CUDA(cudaMalloc((void**)&p.d_unit_row, std::max<size_t>(urow.size(), 1)*4));
+            TFQ_CUDA(cudaMemcpyAsync(p.d_cta_u0, cta_u0.data(), cta_u0.size()*4, cudaMemcpyHostToDevice, stream));
+            TFQ_CUDA(cudaMemcpyAsync(p.d_unit_row, urow.data(), urow.size()*4, cudaMemcpyHostToDevice, stream));
+            TFQ_CUDA(cudaStreamSynchronize(stream));             // the host vectors are locals
+            char const *env_seg = std::getenv("TFQMRGPU_TC_CHAIN");   // entries per accumulation segment
+            int const seg_env = env_seg ? std::atoi(env_seg) : 0;
+            p.tc_seg = (seg_env > 0) ? seg_env : spmm_tc16_default_segment(std::min(LM, 32));
+        } else {
+            TFQ_CUDA(exclusive_scan(p.d_unit_e0, d_cnt.ptr, first.size() + 1, stream));
+        }
         uint32_t ne = 0;
         TFQ_CUDA(cudaMemcpy(&ne, p.d_unit_e0 + p.nUnits, 4, cudaMemcpyDeviceToHost));
         p.nEntries = ne;
@@ -429,6 +524,26 @@ tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, ch
                                                                 nullptr, p.d_unit_e0, p.d_unit_y, p.d_ent_a, p.d_ent_x);
         TFQ_CUDA(cudaStreamSynchronize(stream));
         TFQ_CUDA(cudaGetLastError());
+        if (p.use_tc16 && 64 == LM) {
+            // 64 x 64 blocks: virtual units of 32 x 32 sub-blocks (two per unit, two block columns each, four entries per entry)
+            if (uint64_t(ne)*4 > 0xffffffffull) return TFQ_ERR(TFQMRGPU_STATUS_ALLOCATION_FAILED);
+            uint32_t *e0v = nullptr, *yv = nullptr, *rowv = nullptr, *av = nullptr, *xv = nullptr;
+            size_t const nu = p.nUnits;
+            TFQ_CUDA(cudaMalloc((void**)&e0v, (2*nu + 1)*4)); TFQ_CUDA(cudaMalloc((void**)&yv, std::max<size_t>(4*nu, 1)*4));
+            TFQ_CUDA(cudaMalloc((void**)&rowv, std::max<size_t>(2*nu, 1)*4));
+            TFQ_CUDA(cudaMalloc((void**)&av, std::max<size_t>(4*size_t(ne), 1)*4)); TFQ_CUDA(cudaMalloc((void**)&xv, std::max<size_t>(8*size_t(ne), 1)*4));
+            k_expand_v64<<<nblk(nu + 1, 128), 128, 0, stream>>>(p.nUnits, p.d_unit_e0, p.d_unit_y, p.d_unit_row, p.d_ent_a, p.d_ent_x,
+                                                                e0v, yv, rowv, av, xv);
+            std::vector<uint32_t> cta_u0(size_t(p.tc_grid) + 1);
+            TFQ_CUDA(cudaMemcpyAsync(cta_u0.data(), p.d_cta_u0, cta_u0.size()*4, cudaMemcpyDeviceToHost, stream));
+            TFQ_CUDA(cudaStreamSynchronize(stream));
+            for (auto &v : cta_u0) v *= 2;
+            TFQ_CUDA(cudaMemcpy(p.d_cta_u0, cta_u0.data(), cta_u0.size()*4, cudaMemcpyHostToDevice));
+            TFQ_CUDA(cudaGetLastError());
+            cudaFree(p.d_unit_e0); cudaFree(p.d_unit_y); cudaFree(p.d_unit_row); cudaFree(p.d_ent_a); cudaFree(p.d_ent_x);
+            p.d_unit_e0 = e0v; p.d_unit_y = yv; p.d_unit_row = rowv; p.d_ent_a = av; p.d_ent_x = xv;
+            p.nUnits *= 2; p.nEntries = uint64_t(ne)*4; p.gmax = 2;
+        }
     }
 
     // ---- workspace layout (all pieces 256-byte aligned like the reference's bump allocator) ----------
@@ -439,9 +554,11 @@ tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, ch
         // v1 (X) first, then v4..v9 contiguous so that one memset clears them (core.hxx:114-125)
         p.off_v[1] = take(p.vecBytes);
         for (int v = 4; v <= 9; ++v) p.off_v[v] = take(p.vecBytes);
+        if (p.use_tc16) p.off_xop = take(p.vecBytes);                // fp16 pairs: the same 4 bytes per element
         p.off_v[3]  = take(size_t(p.nnzbX)*2*LM*LN*sizeof(float));   // v3 is always float (core.hxx:60)
         p.off_B     = take(size_t(p.nnzbB)*blockBytes);
-        p.off_A     = take(size_t(p.nnzbA)*2*LM*LM*s);
+        p.off_A     = take(size_t(p.nnzbA)*2*LM*LM*s + (p.use_tc16 ? size_t(p.mb)*4 : 0));
+        p.off_ainv  = p.off_A + size_t(p.nnzbA)*2*LM*LM*s;            // 1/scale of the block rows: part of the 'A' window
         p.off_zero  = take(blockBytes);
         size_t const sc = size_t(nb)*2*LN*s;
         p.off_rho = take(sc); p.off_alfa = take(sc); p.off_beta = take(sc); p.off_c67 = take(sc); p.off_eta = take(sc);
@@ -451,6 +568,11 @@ tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, ch
         p.off_colmon = take(size_t(nb)*4*8);
         p.off_ticket = take((size_t(nb) + 8)*4);
         p.off_ctl    = take(sizeof(Control));
+        if (p.use_tc16) {
+            p.off_xs = take(size_t(nb)*LN*4); p.off_xsinv = take(size_t(nb)*LN*4);
+            p.off_ablkmax = take(size_t(p.nnzbA)*4); p.off_arowscale = take(size_t(p.mb)*4);
+            p.off_xpart = take(size_t(p.nTiles)*64*4);
+        }
         p.bufferBytes = off + 256;
     }
     return TFQMRGPU_STATUS_SUCCESS;

@@ -489,6 +489,11 @@ tfqmrgpuStatus_t launch_spmm(Plan const &p, void *y, void const *x, int expect, 
         int32_t const st = p.user_op(p.user_ctx, y, x, reinterpret_cast<int32_t const*>(&ws<Control const>(p, p.off_ctl)->state), expect, stream);
         return st ? tfqmrgpuStatus_t(st) : TFQMRGPU_STATUS_SUCCESS;
     }
+    if (p.use_tc16) {            // X operand once per product (scales + half pairs, xop.cu), then the tcgen05 product
+        static bool const skip_xop = (nullptr != std::getenv("TFQMRGPU_DEV_SKIP_XOP"));   // dev-only: time the product kernel alone
+        tfqmrgpuStatus_t const st = skip_xop ? TFQMRGPU_STATUS_SUCCESS : launch_xop(p, x, expect, stream);
+        return st ? st : launch_spmm_tc16(p, y, expect, stream);
+    }
     if (p.use_tc) return launch_spmm_tc(p, y, x, expect, stream);
     if (p.use_dmma) return launch_spmm_dmma(p, y, x, expect, stream);
     switch (p.LM*1000 + p.LN) {

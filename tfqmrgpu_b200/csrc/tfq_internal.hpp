@@ -68,6 +68,8 @@ struct Plan {
     uint32_t *d_perm = nullptr;       // caller X index -> storage index
     uint32_t *d_iperm = nullptr;      // storage index -> caller X index
     uint32_t *d_bpos = nullptr;       // storage index of the X block under each B block
+    uint32_t *d_blockcol = nullptr;   // block column of every storage-ordered X block
+    int32_t  *d_rowptrA = nullptr;    // zero-based copy of bsrRowPtrA (row scales of the A operand)
     std::vector<uint32_t> h_colstart; // [nCols+1] first storage block of every block column
     std::vector<int32_t>  h_rowptrX;  // zero-based copy of bsrRowPtrX
     // block-size dependent: vector tiles
@@ -75,7 +77,8 @@ struct Plan {
     uint32_t *d_coltile = nullptr;    // [nCols+1] first tile of every block column
     // block-size dependent: SpMM units (one CTA each): a block row times <= gmax block columns
     uint32_t nUnits = 0, gmax = 1; uint64_t nEntries = 0;
-    bool use_tc = false;              // block-sparse product on the tensor cores (spmm_tc.cu)
+    bool use_tc16 = false;            // block-sparse product on the tensor cores, fp16 operand pairs (spmm_tc16.cu, xop.cu)
+    bool use_tc = false;              // the earlier 3xTF32 tensor-core product (spmm_tc.cu; TFQMRGPU_TENSOR=2)
     bool use_dmma = false;            // complex fp64 product on the FP64 tensor pipe (spmm_dmma.cu)
     tfqmrgpuxOperator_t user_op = nullptr;   // user-defined operator instead of the block-sparse product (ext header)
     void *user_ctx = nullptr;
@@ -84,6 +87,11 @@ struct Plan {
     uint32_t *d_unit_y = nullptr;     // [nUnits*gmax] storage index of the unit's Y blocks (kNoBlock = none)
     uint32_t *d_ent_a = nullptr;      // [nEntries] A block of the entry
     uint32_t *d_ent_x = nullptr;      // [nEntries*gmax] storage index of X blocks (kNoBlock = structural zero)
+    // fp16-pair tensor-core product: units dealt to `tc_grid` persistent CTAs and stored CTA by CTA
+    uint32_t *d_cta_u0 = nullptr;     // [tc_grid+1] first unit of every CTA
+    uint32_t *d_unit_row = nullptr;   // [nUnits] block row of the unit (scale of the A operand)
+    uint32_t tc_grid = 0;
+    int      tc_seg = 16;             // entries per accumulation segment
 
     // ---- caller-owned workspace ------------------------------------------------------------------
     char  *pBuffer = nullptr;
@@ -94,6 +102,9 @@ struct Plan {
     size_t off_rho = 0, off_alfa = 0, off_beta = 0, off_c67 = 0, off_eta = 0;
     size_t off_tau = 0, off_var = 0, off_invBn2 = 0, off_status = 0, off_snap = 0;
     size_t off_part = 0, off_colmon = 0, off_ticket = 0, off_ctl = 0;
+    // fp16-pair operands (xop.cu): X operand, column scales and inverses, row scale inverses of A (directly behind the A
+    // blocks, inside the 'A' window), block maxima and row scales of A, tile maxima of the X operand
+    size_t off_xop = 0, off_xs = 0, off_xsinv = 0, off_ainv = 0, off_ablkmax = 0, off_arowscale = 0, off_xpart = 0;
     size_t vecBytes = 0;              // bytes of one X-shaped vector
 
     // ---- host side ---------------------------------------------------------------------------
@@ -105,6 +116,7 @@ struct Plan {
     cudaGraphExec_t body_exec = nullptr;
     cudaStream_t    capture_stream = nullptr;
     cudaStream_t    copy_stream = nullptr;     // uploads of large operands, overlapped chunk-wise with their layout conversion
+    cudaEvent_t     chunk_ev[3] = {nullptr};   // order the chunk uploads and their conversions (owned by the plan: no leak on error paths)
 
     // ---- stats (tfqmrgpu_plan.hxx:41-45) -------------------------------------------------------
     double residuum_reached = 0, flops_performed = -1, flops_performed_all = 0;
@@ -131,6 +143,14 @@ tfqmrgpuStatus_t launch_spmm(Plan const &p, void *y, void const *x, int expect, 
 bool spmm_tc_supported(int LM, int LN, char precision, int level);
 int  spmm_tc_columns_per_unit(int LN);
 tfqmrgpuStatus_t launch_spmm_tc(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream);
+// fp16-pair tensor-core variant (spmm_tc16.cu, the default for complex fp32 with LM, LN in {16, 32, 64}) and its operands (xop.cu)
+bool spmm_tc16_supported(int LM, int LN, char precision, int level);
+int  spmm_tc16_columns_per_unit(int LM, int LN);
+int  spmm_tc16_default_segment(int LM);
+tfqmrgpuStatus_t launch_spmm_tc16(Plan const &p, void *y, int expect, cudaStream_t stream);
+tfqmrgpuStatus_t launch_xop(Plan const &p, void const *x, int expect, cudaStream_t stream);          // X operand from a vector
+tfqmrgpuStatus_t launch_aop_blockmax(Plan const &p, uint32_t b0, uint32_t nb, cudaStream_t stream);  // per uploaded chunk of A
+tfqmrgpuStatus_t launch_aop_convert(Plan const &p, cudaStream_t stream);                            // after the last chunk
 // DMMA variant (spmm_dmma.cu): complex fp64, LM and LN in {16, 32, 64}; also switched off by TFQMRGPU_TENSOR=0
 bool spmm_dmma_supported(int LM, int LN, char precision);
 int  spmm_dmma_columns_per_unit(int LM, int LN);
