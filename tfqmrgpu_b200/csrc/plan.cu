@@ -572,6 +572,7 @@ tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, ch
             p.off_xs = take(size_t(nb)*LN*4); p.off_xsinv = take(size_t(nb)*LN*4);
             p.off_ablkmax = take(size_t(p.nnzbA)*4); p.off_arowscale = take(size_t(p.mb)*4);
             p.off_xpart = take(size_t(p.nTiles)*64*4);
+            p.off_mx = take(3*size_t(nb)*LN*4);                       // column maxima of |v4|, |v5|, |v6| (vecops.cu)
         }
         p.bufferBytes = off + 256;
     }

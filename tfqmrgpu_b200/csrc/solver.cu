@@ -33,15 +33,20 @@ tfqmrgpuStatus_t enqueue_body(Plan &p, cudaStream_t stream, cudaEvent_t const *e
     void *const v8 = p.pBuffer + p.off_v[8], *const v9 = p.pBuffer + p.off_v[9];
     tfqmrgpuStatus_t st;
 #define TFQ_DO(call) do { st = (call); if (TFQMRGPU_STATUS_SUCCESS != st) return st; } while (0)
-    TFQ_DO(launch_vecop(p, OP_K1, stream));
+    // plans on the fp16-pair tensor-core product: K1 and K3 write v6 AND its tensor-core operand (TFQMRGPU_XOP_FUSED=0: separate pass)
+    static bool const fuse_env = [] { char const *e = std::getenv("TFQMRGPU_XOP_FUSED"); return !(e && '0' == e[0]); }();
+    bool const fused = p.use_tc16 && fuse_env && nullptr == p.user_op;
+    TFQ_DO(fused ? launch_vecop_xop(p, OP_K1, stream) : launch_vecop(p, OP_K1, stream));
     if (events) TFQ_CUDA(cudaEventRecord(events[0], stream));
-    TFQ_DO(launch_spmm(p, v9, v6, STATE_RUN, stream));                 // v9 := A*v6     (core.hxx:198)
+    TFQ_DO(fused ? launch_spmm_operand_ready(p, v9, v6, STATE_RUN, stream)
+                 : launch_spmm(p, v9, v6, STATE_RUN, stream));         // v9 := A*v6     (core.hxx:198)
     if (events) TFQ_CUDA(cudaEventRecord(events[1], stream));
     TFQ_DO(launch_vecop(p, OP_E1, stream));
     TFQ_DO(launch_vecop(p, OP_K2, stream));
-    TFQ_DO(launch_vecop(p, OP_K3, stream));
+    TFQ_DO(fused ? launch_vecop_xop(p, OP_K3, stream) : launch_vecop(p, OP_K3, stream));
     if (events) TFQ_CUDA(cudaEventRecord(events[2], stream));
-    TFQ_DO(launch_spmm(p, v8, v6, STATE_RUN, stream));                 // v8 := A*v6     (core.hxx:224)
+    TFQ_DO(fused ? launch_spmm_operand_ready(p, v8, v6, STATE_RUN, stream)
+                 : launch_spmm(p, v8, v6, STATE_RUN, stream));         // v8 := A*v6     (core.hxx:224)
     if (events) TFQ_CUDA(cudaEventRecord(events[3], stream));
     TFQ_DO(launch_vecop(p, OP_E2, stream));
     TFQ_DO(launch_vecop(p, OP_K4, stream));
@@ -123,6 +128,7 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
     TFQ_CUDA(cudaMemsetAsync(p.pBuffer + p.off_ticket, 0, (size_t(p.nCols) + 8)*4, stream));
     // v1 and v4..v9 are contiguous: the initial guess is discarded like in the reference (core.hxx:125)
     TFQ_CUDA(cudaMemsetAsync(p.pBuffer + p.off_v[1], 0, (p.off_v[9] + p.vecBytes) - p.off_v[1], stream));
+    if (p.use_tc16) TFQ_CUDA(cudaMemsetAsync(p.pBuffer + p.off_mx, 0, 3*size_t(p.nCols)*p.LN*sizeof(float), stream));   // max|v6| = 0
 
     tfqmrgpuStatus_t st;
 #define TFQ_DO(call) do { st = (call); if (TFQMRGPU_STATUS_SUCCESS != st) return st; launches += 1; } while (0)

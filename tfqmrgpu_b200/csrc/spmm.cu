@@ -483,6 +483,12 @@ tfqmrgpuStatus_t launch_sized(Plan const &p, void *y, void const *x, int expect,
 
 } // namespace
 
+tfqmrgpuStatus_t launch_spmm_operand_ready(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream)
+{
+    if (p.use_tc16 && nullptr == p.user_op) return launch_spmm_tc16(p, y, expect, stream);
+    return launch_spmm(p, y, x, expect, stream);
+}
+
 tfqmrgpuStatus_t launch_spmm(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream)
 {
     if (p.user_op) {             // tfqmrgpux_bsrsv_setOperator: the caller's Y = A*X

@@ -165,6 +165,18 @@ __device__ __forceinline__ uint64_t smem_desc_noswizzle(uint32_t saddr, uint32_t
 #define TFQ_TC16_ABLATE 0
 #endif
 
+// dev-only per-role cycle accounting of CTA 0 (scripts/dev_tc16_trace.py): where every role's time goes, summed over the launch
+#ifdef TFQ_TC16_TRACE
+__device__ long long g_tc16_trace[8*8];
+#define TR_DECL long long tr_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tr_t = clock64()
+#define TR_LAP(k) do { long long const n_ = clock64(); tr_[k] += n_ - tr_t; tr_t = n_; } while (0)
+#define TR_DUMP(role) do { if (0 == blockIdx.x && 0 == lane) { for (int k_ = 0; k_ < 8; ++k_) g_tc16_trace[(role)*8 + k_] = tr_[k_]; } } while (0)
+#else
+#define TR_DECL do { } while (0)
+#define TR_LAP(k) do { } while (0)
+#define TR_DUMP(role) do { } while (0)
+#endif
+
 template <int LM, int LN> struct Tc16Shape {
     static constexpr int G   = 64/LN;                   // block columns per unit: 128 MMA rows = G * 2 * LN
     static constexpr int KS  = LM/16;                   // MMA k-steps per entry
@@ -204,23 +216,24 @@ spmm_tc16_kernel(Tc16Args const a)
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t *const bar_a_full   = reinterpret_cast<uint64_t*>(smem_raw);   // [RA] A block has landed
-    uint64_t *const bar_a_free   = bar_a_full + RA;                          // [RA] the MMAs that read the slot have completed
-    uint64_t *const bar_x_full   = bar_a_free + RA;                          // [NS] X operand of the stage is in TMEM
-    uint64_t *const bar_x_free   = bar_x_full + NS;                          // [NS] the MMAs that read the stage have completed
-    uint64_t *const bar_acc_full = bar_x_free + NS;                          // [2]  a segment's MMAs have completed
+    uint64_t *const bar_done     = bar_a_full + RA;                          // [RA] the MMAs of the entry have completed: its A slot
+                                                                             //      (entry n + RA) and its X stage (entry n + NS) are free
+    uint64_t *const bar_x_full   = bar_done + RA;                            // [NS] X operand of the stage is in TMEM
+    uint64_t *const bar_acc_full = bar_x_full + NS;                          // [2]  a segment's MMAs have completed
     uint64_t *const bar_acc_free = bar_acc_full + 2;                         // [2]  the epilogue has read the set
     uint32_t *const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 1008);
     unsigned char *const ring = smem_raw + 1024;
     float *const exch0 = reinterpret_cast<float*>(smem_raw + 1024 + size_t(RA)*S::ABYTES);
-    static_assert((2*RA + 2*NS + 4)*8 <= 1008, "barrier area");
+    static_assert((2*RA + NS + 4)*8 <= 1008, "barrier area");
+    static_assert(RA >= NS, "one ring of completion barriers serves the A slots and the X stages");
 
     int const tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     int const gs = a.gstride;
 
     if (kMmaWarp == w) tmem_alloc(tmem_slot, S::TMEM_COLS);
     if (0 == tid) {
-        for (int r = 0; r < RA; ++r) { mbar_init(&bar_a_full[r], 1); mbar_init(&bar_a_free[r], 1); }
-        for (int s = 0; s < NS; ++s) { mbar_init(&bar_x_full[s], kWarpsPerGroup); mbar_init(&bar_x_free[s], 1); }
+        for (int r = 0; r < RA; ++r) { mbar_init(&bar_a_full[r], 1); mbar_init(&bar_done[r], 1); }
+        for (int s = 0; s < NS; ++s) mbar_init(&bar_x_full[s], kWarpsPerGroup);
         for (int c = 0; c < 2; ++c)  { mbar_init(&bar_acc_full[c], 1); mbar_init(&bar_acc_free[c], kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -241,13 +254,16 @@ spmm_tc16_kernel(Tc16Args const a)
         uint32_t const leader = elect_one_sync();
         uint64_t const stream_once = policy_evict_first();   // A is read once per product: keep it from displacing X in L2
         uint32_t n = 0;
+        TR_DECL;
         for (uint32_t eb = 0; eb < total; eb += 32) {
             uint32_t const ia_l = (eb + lane < total) ? a.ent_a[E0 + eb + lane] : 0u;
             uint32_t const cnt = (total - eb < 32u) ? (total - eb) : 32u;
             for (uint32_t t = 0; t < cnt; ++t, ++n) {
                 uint32_t const ia = __shfl_sync(0xffffffffu, ia_l, int(t));
                 uint32_t const r = n & (RA - 1), use = n / RA;
-                if (use > 0) mbar_wait(&bar_a_free[r], (use - 1) & 1);
+                TR_LAP(1);
+                if (use > 0) mbar_wait(&bar_done[r], (use - 1) & 1);
+                TR_LAP(0);
                 if (leader) {
                     if (TFQ_TC16_ABLATE & 8) mbar_arrive(&bar_a_full[r]);
                     else {
@@ -258,6 +274,8 @@ spmm_tc16_kernel(Tc16Args const a)
                 __syncwarp();
             }
         }
+        TR_LAP(1);
+        TR_DUMP(0);
     } else if (kMmaWarp == w) {
         // ================= MMA warp: one elected lane issues ==========================================================
         uint32_t const leader = elect_one_sync();
@@ -265,6 +283,7 @@ spmm_tc16_kernel(Tc16Args const a)
         uint32_t n = 0, sg = 0;
         uint32_t e_begin = E0;
         uint32_t e_end_next = (u0 < u1) ? a.unit_e0[u0 + 1] : E0;
+        TR_DECL;
         for (uint32_t u = u0; u < u1; ++u) {
             uint32_t const e_end = e_end_next;
             if (u + 1 < u1) e_end_next = a.unit_e0[u + 2];          // one unit ahead: not on the critical path
@@ -274,30 +293,45 @@ spmm_tc16_kernel(Tc16Args const a)
             for (int s = 0; s < nSeg; ++s, ++sg) {
                 int const len = (nE*(s + 1))/nSeg - (nE*s)/nSeg;
                 uint32_t const c = sg & 1, cuse = sg >> 1;
+                TR_LAP(3);
                 if (cuse > 0) { mbar_wait(&bar_acc_free[c], (cuse - 1) & 1); tc_fence_after(); }
+                TR_LAP(2);
                 uint32_t const acc = tmem_base + S::ACC0 + c*NB;
+                // The correction sum D' of a set lives for the whole unit (its truncation errors carry the factor 1/2048); the main
+                // sum D starts afresh with every segment.  First use of the set in this unit: one MMA of N' = 2N initialises both.
+                bool const fresh = (s < 2);
                 for (int t = 0; t < len; ++t, ++n) {
                     uint32_t const r = n & (RA - 1), st = n & (NS - 1);
-                    mbar_wait(&bar_a_full[r], (n / RA) & 1);
-                    mbar_wait(&bar_x_full[st], (n / NS) & 1);
+                    bool const a_ok = mbar_try_wait(&bar_a_full[r], (n / RA) & 1);      // both tests in flight together
+                    bool const x_ok = mbar_try_wait(&bar_x_full[st], (n / NS) & 1);
+                    if (!a_ok) mbar_wait(&bar_a_full[r], (n / RA) & 1);
+                    if (!x_ok) mbar_wait(&bar_x_full[st], (n / NS) & 1);
                     tc_fence_after();
+                    TR_LAP(0);
                     if (leader) {
                         uint32_t const sa = ring_u32 + r*S::ABYTES;
                         uint32_t const xa = tmem_base + S::STAGE0 + st*SC;
                         #pragma unroll
                         for (int ks = 0; ks < ((TFQ_TC16_ABLATE & 4) ? 0 : KS); ++ks) {
                             uint64_t const b = smem_desc_noswizzle(sa + ks*2*S::SLAB, S::SLAB, 128);
-                            mma_f16_ts(acc,     xa + 8*ks,        b, IDESC_NB, (t > 0 || ks > 0) ? 1u : 0u);   // Xhi * [Ahi ; Alo] -> [D | D']
-                            mma_f16_ts(acc + N, xa + LM/2 + 8*ks, b, IDESC_N,  1u);                              // Xlo * Ahi        ->      D'
+                            if (0 == ks && 0 == t && !fresh) {
+                                uint64_t const blo = smem_desc_noswizzle(sa + N*16, S::SLAB, 128);           // rows [N, 2N): Alo
+                                mma_f16_ts(acc,     xa, b,   IDESC_N, 0u);                                    // Xhi * Ahi  -> D (restart)
+                                mma_f16_ts(acc + N, xa, blo, IDESC_N, 1u);                                    // Xhi * Alo  -> D' (continue)
+                            } else {
+                                mma_f16_ts(acc, xa + 8*ks, b, IDESC_NB, (t > 0 || ks > 0) ? 1u : 0u);         // Xhi * [Ahi ; Alo] -> [D | D']
+                            }
+                            mma_f16_ts(acc + N, xa + LM/2 + 8*ks, b, IDESC_N, 1u);                            // Xlo * Ahi         ->      D'
                         }
-                        mma_commit(&bar_x_free[st]);
-                        mma_commit(&bar_a_free[r]);
+                        mma_commit(&bar_done[r]);
                         if (t == len - 1) mma_commit(&bar_acc_full[c]);
                     }
                     __syncwarp();
+                    TR_LAP(1);
                 }
             }
         }
+        TR_DUMP(1);
     } else if (w < kConvWarps) {
         // ================= converter warps: X operand rows -> registers -> tensor memory =================================
         // Group grp takes the entries n = grp (mod 2) of the CTA's flat entry range; its 4 warps cover the 128 TMEM lanes
@@ -310,6 +344,7 @@ spmm_tc16_kernel(Tc16Args const a)
         uint32_t const lane_base = tmem_base + (uint32_t(32*q4) << 16) + S::STAGE0;
         uint32_t const nOwn = (total > uint32_t(grp)) ? (total - grp + kConvGroups - 1)/kConvGroups : 0u;
 
+        TR_DECL;
         auto index_of = [&](uint32_t k) -> uint32_t {    // X block of own entry k (kNoBlock: structural zero)
             return (has_g && k < nOwn) ? a.ent_x[size_t(E0 + grp + kConvGroups*k)*gs + g] : kNoBlock;
         };
@@ -325,8 +360,10 @@ spmm_tc16_kernel(Tc16Args const a)
         };
         auto put = [&](uint32_t k, uint4 const (&b)[NCH]) {
             uint32_t const n = grp + kConvGroups*k;      // entry number within the CTA
-            uint32_t const st = n & (NS - 1), use = n / NS;
-            if (use > 0) { mbar_wait(&bar_x_free[st], (use - 1) & 1); tc_fence_after(); }
+            uint32_t const st = n & (NS - 1);
+            TR_LAP(3);
+            if (n >= uint32_t(NS)) { mbar_wait(&bar_done[(n - NS) & (RA - 1)], ((n - NS) / RA) & 1); tc_fence_after(); }   // the stage's previous entry
+            TR_LAP(0);
             if (!(TFQ_TC16_ABLATE & 2)) {
                 uint32_t const *r = reinterpret_cast<uint32_t const*>(&b[0]);
                 if (32 == LM) tmem_st32(lane_base + st*SC, r); else tmem_st16(lane_base + st*SC, r);
@@ -335,6 +372,7 @@ spmm_tc16_kernel(Tc16Args const a)
             tc_fence_before();
             __syncwarp();
             if (0 == lane) mbar_arrive(&bar_x_full[st]);
+            TR_LAP(1);
         };
 
         if (nOwn > 0) {
@@ -351,6 +389,8 @@ spmm_tc16_kernel(Tc16Args const a)
                 }
             }
         }
+        TR_LAP(3);
+        if (0 == q4) TR_DUMP(2 + grp);
     } else {
         // ================= epilogue warps: accumulator segments -> registers (fp32 sums) -> Y ==========================
         int const ew = w - kConvWarps, q4 = ew & 3, h = ew >> 2;      // h: Re|Im of A = half of the accumulator columns
@@ -360,6 +400,7 @@ spmm_tc16_kernel(Tc16Args const a)
         uint32_t sg = 0;
         uint32_t e_begin = E0;
         uint32_t e_end_next = (u0 < u1) ? a.unit_e0[u0 + 1] : E0;
+        TR_DECL;
         for (uint32_t u = u0; u < u1; ++u) {
             uint32_t const e_end = e_end_next;
             if (u + 1 < u1) e_end_next = a.unit_e0[u + 2];
@@ -372,21 +413,30 @@ spmm_tc16_kernel(Tc16Args const a)
             for (int i = 0; i < LM; ++i) acc[i] = 0.f;
             for (int s = 0; s < nSeg; ++s, ++sg) {
                 uint32_t const c = sg & 1;
+                TR_LAP(2);
                 mbar_wait(&bar_acc_full[c], (sg >> 1) & 1);
                 tc_fence_after();
+                TR_LAP(0);
+                bool const with_corr = (s + 2 >= nSeg);          // last segment of this unit in set c: its D' is complete
                 #pragma unroll
                 for (int ch = 0; ch < LM/16; ++ch) {
                     uint32_t d[16], d2[16];
                     tmem_ld16(lane_base + c*NB + 16*ch, d);
-                    tmem_ld16(lane_base + c*NB + N + 16*ch, d2);
+                    if (with_corr) tmem_ld16(lane_base + c*NB + N + 16*ch, d2);
                     tmem_wait_ld();
-                    #pragma unroll
-                    for (int i = 0; i < 16; ++i)   // main + correction/2048, then the running sum: both rounded to nearest
-                        acc[16*ch + i] += fmaf(__uint_as_float(d2[i]), 1.f/2048.f, __uint_as_float(d[i]));
+                    if (with_corr) {
+                        #pragma unroll
+                        for (int i = 0; i < 16; ++i)   // main + correction/2048, then the running sum: both rounded to nearest
+                            acc[16*ch + i] += fmaf(__uint_as_float(d2[i]), 1.f/2048.f, __uint_as_float(d[i]));
+                    } else {
+                        #pragma unroll
+                        for (int i = 0; i < 16; ++i) acc[16*ch + i] += __uint_as_float(d[i]);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (0 == lane) mbar_arrive(&bar_acc_free[c]);
+                TR_LAP(1);
             }
             // combine the four real products: Yr = XrAr - XiAi ; Yi = XrAi + XiAr.  Threads with Im(X) rows hand their sums
             // to the threads with the Re(X) rows of the same column j through shared memory (two buffers alternate by unit,
@@ -414,7 +464,9 @@ spmm_tc16_kernel(Tc16Args const a)
                 for (int i = 0; i < LM; ++i)
                     yp[i*YS] = (acc[i] + sgn*exch[((g*2 + (1 - h))*LM + i)*LN + j])*scale;
             }
+            TR_LAP(2);
         }
+        if (0 == ew) TR_DUMP(4);
     }
     tc_fence_before();
     __syncthreads();
@@ -467,3 +519,9 @@ tfqmrgpuStatus_t launch_spmm_tc16(Plan const &p, void *y, int expect, cudaStream
 }
 
 } // namespace tfq
+
+#ifdef TFQ_TC16_TRACE
+extern "C" int tfq_tc16_trace_dump(long long *host, int n) {
+    return int(cudaMemcpyFromSymbol(host, tfq::g_tc16_trace, size_t(n)*sizeof(long long)));
+}
+#endif

@@ -104,7 +104,7 @@ struct Plan {
     size_t off_part = 0, off_colmon = 0, off_ticket = 0, off_ctl = 0;
     // fp16-pair operands (xop.cu): X operand, column scales and inverses, row scale inverses of A (directly behind the A
     // blocks, inside the 'A' window), block maxima and row scales of A, tile maxima of the X operand
-    size_t off_xop = 0, off_xs = 0, off_xsinv = 0, off_ainv = 0, off_ablkmax = 0, off_arowscale = 0, off_xpart = 0;
+    size_t off_xop = 0, off_xs = 0, off_xsinv = 0, off_ainv = 0, off_ablkmax = 0, off_arowscale = 0, off_xpart = 0, off_mx = 0;
     size_t vecBytes = 0;              // bytes of one X-shaped vector
 
     // ---- host side ---------------------------------------------------------------------------
@@ -148,6 +148,8 @@ bool spmm_tc16_supported(int LM, int LN, char precision, int level);
 int  spmm_tc16_columns_per_unit(int LM, int LN);
 int  spmm_tc16_default_segment(int LM);
 tfqmrgpuStatus_t launch_spmm_tc16(Plan const &p, void *y, int expect, cudaStream_t stream);
+// y = A*x where the X operand of x already exists (written by launch_vecop_xop)
+tfqmrgpuStatus_t launch_spmm_operand_ready(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream);
 tfqmrgpuStatus_t launch_xop(Plan const &p, void const *x, int expect, cudaStream_t stream);          // X operand from a vector
 tfqmrgpuStatus_t launch_aop_blockmax(Plan const &p, uint32_t b0, uint32_t nb, cudaStream_t stream);  // per uploaded chunk of A
 tfqmrgpuStatus_t launch_aop_convert(Plan const &p, cudaStream_t stream);                            // after the last chunk
@@ -158,6 +160,8 @@ tfqmrgpuStatus_t launch_spmm_dmma(Plan const &p, void *y, void const *x, int exp
 // fused vector algebra, see vecops.cu
 enum VecOp : int { OP_INIT = 0, OP_K1, OP_E1, OP_K2, OP_K3, OP_E2, OP_K4, OP_N3, OP_COUNT };
 tfqmrgpuStatus_t launch_vecop(Plan const &p, int op, cudaStream_t stream);
+// OP_K1 / OP_K3 that also emit the X operand of the fp16-pair tensor-core product from the v6 they write
+tfqmrgpuStatus_t launch_vecop_xop(Plan const &p, int op, cudaStream_t stream);
 // v[bpos[b]] += scal * B[b]   (linalg.hxx:383-428)
 tfqmrgpuStatus_t launch_add_rhs(Plan const &p, void *v, double scal, int expect, cudaStream_t stream);
 // host layout <-> internal layout (layout.cu)

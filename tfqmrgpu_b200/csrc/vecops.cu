@@ -20,6 +20,8 @@
 // evaluates the reference's probe rule on the device, so no host round trip is needed per iteration.
 // Everything is deterministic (no floating-point atomics).
 #include "tfq_internal.hpp"
+#include <cuda_fp16.h>
+#include <type_traits>
 
 namespace tfq {
 
@@ -40,6 +42,10 @@ template <typename real_t> struct VecArgs {
     uint32_t const *coltile;
     uint32_t nCols;
     int LM, LN, lmShift;
+    // fp16-pair operand of the tensor-core product (xop.cu, spmm_tc16.cu): per-column maxima of |v4|, |v5|, |v6| kept by the kernels
+    // that write those vectors, tile maxima scratch, and the operand itself with its column scales (written by K1 / K3)
+    float *mx4, *mx5, *mx6, *partmax, *xs, *xsinv;
+    uint4 *xop;
 };
 
 template <typename T, int N> struct alignas(sizeof(T)*N) Vec { T v[N]; };
@@ -119,7 +125,9 @@ template <> struct OpTraits<OP_E2>   { static constexpr int D = 1, expect = STAT
 template <> struct OpTraits<OP_K4>   { static constexpr int D = 2, expect = STATE_RUN; };
 template <> struct OpTraits<OP_N3>   { static constexpr int D = 1, expect = STATE_PROBE; };
 
-template <typename real_t, int VEC, int OP>
+// XM: also keep the per-column maximum magnitude of the vector this kernel writes (INIT, K2, E2: v5; E1: v4) - the
+// operand-emitting K1 / K3 (vec_xop_kernel) bound the magnitude of their result with it
+template <typename real_t, int VEC, int OP, bool XM>
 __global__ void __launch_bounds__(256)
 vec_kernel(VecArgs<real_t> const a)
 {
@@ -153,11 +161,15 @@ vec_kernel(VecArgs<real_t> const a)
     if (OP == OP_K4) coef(a.eta, pr, pi);
 
     double acc[DD][VEC];
+    float vmax[VEC];
     #pragma unroll
     for (int d = 0; d < DD; ++d) {
         #pragma unroll
         for (int v = 0; v < VEC; ++v) acc[d][v] = 0;
     }
+    #pragma unroll
+    for (int v = 0; v < VEC; ++v) vmax[v] = 0.f;
+    (void)vmax;
 
     int const nrows = int(t.b1 - t.b0) << a.lmShift;
     #pragma unroll 2
@@ -175,6 +187,7 @@ vec_kernel(VecArgs<real_t> const a)
             #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 acc[0][v] += double(xr.v[v])*double(xr.v[v]) + double(xi.v[v])*double(xi.v[v]);
+                if (XM) vmax[v] = fmaxf(vmax[v], fmaxf(fabsf(float(xr.v[v])), fabsf(float(xi.v[v]))));
                 real_t const tr = xr.v[v]*wr.v[v] - xi.v[v]*wi.v[v];
                 real_t const ti = xr.v[v]*wi.v[v] + xi.v[v]*wr.v[v];
                 acc[1 % DD][v] += double(tr); acc[2 % DD][v] += double(ti);
@@ -203,6 +216,7 @@ vec_kernel(VecArgs<real_t> const a)
                 real_t const nr = br.v[v] + pr[v]*tr - pi[v]*ti;
                 real_t const ni = bi.v[v] + pi[v]*tr + pr[v]*ti;
                 yr.v[v] = nr; yi.v[v] = ni;
+                if (XM) vmax[v] = fmaxf(vmax[v], fmaxf(fabsf(float(nr)), fabsf(float(ni))));
                 real_t const dr = nr*wr.v[v] - ni*wi.v[v]; // linalg.hxx:506-507, products in real_t x float
                 real_t const di = nr*wi.v[v] + ni*wr.v[v];
                 acc[0][v] += double(dr); acc[1 % DD][v] += double(di);
@@ -222,6 +236,7 @@ vec_kernel(VecArgs<real_t> const a)
                 real_t const mr = qr[v]*br.v[v] - qi[v]*bi.v[v] + zr.v[v]; // linalg.hxx:656-657
                 real_t const mi = qi[v]*br.v[v] + qr[v]*bi.v[v] + zi.v[v];
                 zr.v[v] = mr; zi.v[v] = mi;
+                if (XM) vmax[v] = fmaxf(vmax[v], fmaxf(fabsf(float(mr)), fabsf(float(mi))));
                 acc[0][v] += double(mr)*double(mr) + double(mi)*double(mi);
             }
             stv<real_t, VEC>(a.v7 + ore, yr); stv<real_t, VEC>(a.v7 + oim, yi);
@@ -255,6 +270,7 @@ vec_kernel(VecArgs<real_t> const a)
                 real_t const mr = pr[v]*br.v[v] - pi[v]*bi.v[v] + zr.v[v];
                 real_t const mi = pi[v]*br.v[v] + pr[v]*bi.v[v] + zi.v[v];
                 zr.v[v] = mr; zi.v[v] = mi;
+                if (XM) vmax[v] = fmaxf(vmax[v], fmaxf(fabsf(float(mr)), fabsf(float(mi))));
                 acc[0][v] += double(mr)*double(mr) + double(mi)*double(mi);
             }
             stv<real_t, VEC>(a.v5 + ore, zr); stv<real_t, VEC>(a.v5 + oim, zi);
@@ -310,6 +326,26 @@ vec_kernel(VecArgs<real_t> const a)
         }
     }
 
+    if (XM) {   // tile maximum per lane j (the order of a maximum does not matter)
+        float *const fr = reinterpret_cast<float*>(red);
+        __syncthreads();
+        #pragma unroll
+        for (int v = 0; v < VEC; ++v) fr[r0*LN + j0 + v] = vmax[v];
+        __syncthreads();
+        int hm = 1; while (hm < rstep) hm <<= 1;
+        for (hm >>= 1; hm > 0; hm >>= 1) {
+            if (r0 < hm && r0 + hm < rstep) {
+                #pragma unroll
+                for (int v = 0; v < VEC; ++v) fr[r0*LN + j0 + v] = fmaxf(fr[r0*LN + j0 + v], fr[(r0 + hm)*LN + j0 + v]);
+            }
+            __syncthreads();
+        }
+        if (0 == r0 && tid < LNV) {
+            #pragma unroll
+            for (int v = 0; v < VEC; ++v) a.partmax[size_t(blockIdx.x)*64 + j0 + v] = fr[j0 + v];
+        }
+    }
+
     // ---- the last tile of this block column finishes the column ------------------------------------
     uint32_t const t0 = a.coltile[c], t1 = a.coltile[c + 1];
     __threadfence();
@@ -320,6 +356,12 @@ vec_kernel(VecArgs<real_t> const a)
     __threadfence();
     if (0 == tid) a.ticket[c] = 0;
 
+    if (XM && tid < LN) {
+        float m = 0.f;
+        for (uint32_t tt = t0; tt < t1; ++tt) m = fmaxf(m, __ldcg(&a.partmax[size_t(tt)*64 + tid]));
+        float *const mx = (OP == OP_E1) ? a.mx4 : a.mx5;
+        mx[size_t(c)*LN + tid] = m;
+    }
     int const nq = DD*LN;
     int const nsl = int(blockDim.x)/nq;
     {
@@ -469,6 +511,155 @@ vec_kernel(VecArgs<real_t> const a)
     }
 }
 
+// ---- K1 / K3 with the tensor-core operand -----------------------------------------------------------
+// Both write v6, the vector the next block-sparse product multiplies.  For plans on the fp16-pair tensor-core product they
+// also emit v6 as that product's X operand (layout and number format: xop.cu), so that the operand costs one more vector
+// WRITE per product instead of a pass of its own.  The column scale comes from a bound on the result's magnitude,
+//   K1: max|v6'| <= max|v5| + (|Re beta| + |Im beta|) max|v6|      K3: max|v6'| <= max|v6| + (|Re alfa| + |Im alfa|) max|v4|
+// (maxima over Re and Im parts, kept per column by the kernels that wrote those vectors), so no second pass is needed; fp16
+// being a floating-point format, a bound that is loose by a few binades costs range (29 binades are there), not precision.
+// Thread = (k-octet, lane j): its 8 k values of Re and Im are the 16-byte chunks of the operand rows (Re, j) and (Im, j);
+// all global accesses are coalesced over j.  The arithmetic statements are those of vec_kernel (reference: core.hxx:194,216-220).
+__device__ __forceinline__ float xop_scale_for_bound(float bound) {
+    float const b = bound*1.0001f;                       // (the bound itself was rounded)
+    if (!(b > 0.f) || !(b <= 3.0e38f)) return 1.f;
+    int ex;
+    frexpf(b, &ex);
+    int e = 15 - ex;
+    e = (e > 120) ? 120 : ((e < -120) ? -120 : e);
+    return ldexpf(1.f, e);
+}
+__device__ __forceinline__ uint32_t xop_pack2(__half a, __half b) {
+    return uint32_t(__half_as_ushort(a)) | (uint32_t(__half_as_ushort(b)) << 16);
+}
+
+template <int OP, int LM, int LN>
+__global__ void __launch_bounds__(256)
+vec_xop_kernel(VecArgs<float> const a)
+{
+    static_assert(OP == OP_K1 || OP == OP_K3, "the kernels that write v6");
+    if (a.ctl->state != STATE_RUN) return;
+    constexpr int SUBS = 256/LN;                 // items in flight per CTA
+    constexpr int KO = LM/8;                     // k-octets per block
+    __shared__ float s_max[256];
+    __shared__ int s_last;
+
+    Tile const t = a.tiles[blockIdx.x];
+    uint32_t const c = t.col;
+    int const tid = threadIdx.x, j = tid % LN, sub = tid / LN;
+    size_t const sj = (size_t(c)*2 + 0)*LN + j, sji = (size_t(c)*2 + 1)*LN + j;
+
+    float pr = 0, pi = 0, qr = 0, qi = 0, sr = 0, si = 0, bound;
+    if (OP == OP_K1) {
+        pr = a.beta[sj]; pi = a.beta[sji];
+        bound = a.mx5[size_t(c)*LN + j] + (fabsf(pr) + fabsf(pi))*a.mx6[size_t(c)*LN + j];
+    } else {
+        pr = a.eta[sj]; pi = a.eta[sji]; qr = a.alfa[sj]; qi = a.alfa[sji]; sr = a.c67[sj]; si = a.c67[sji];
+        bound = a.mx6[size_t(c)*LN + j] + (fabsf(qr) + fabsf(qi))*a.mx4[size_t(c)*LN + j];
+    }
+    (void)qr; (void)qi; (void)sr; (void)si;
+    float const scale = xop_scale_for_bound(bound);
+    if (blockIdx.x == a.coltile[c] && 0 == sub) { a.xs[size_t(c)*LN + j] = scale; a.xsinv[size_t(c)*LN + j] = 1.f/scale; }
+
+    float vmax = 0.f;
+    int const nItems = int(t.b1 - t.b0)*KO;
+    constexpr size_t plane = size_t(LM)*LN;
+    for (int it = sub; it < nItems; it += SUBS) {
+        uint32_t const blk = t.b0 + uint32_t(it / KO);
+        int const ko = it % KO;
+        size_t const ore = (size_t(blk)*2*LM + 8*ko)*LN + j, oim = ore + plane;
+        float zr[8], zi[8];                       // the new v6
+        if (OP == OP_K1) {    // v6 := v5 + beta*v6   (core.hxx:194, linalg.hxx:660-661)
+            float xr[8], xi[8];
+            #pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                xr[kk] = a.v5[ore + kk*LN]; xi[kk] = a.v5[oim + kk*LN];
+                zr[kk] = a.v6[ore + kk*LN]; zi[kk] = a.v6[oim + kk*LN];
+            }
+            #pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                float const nr = xr[kk] + pr*zr[kk] - pi*zi[kk];
+                float const ni = xi[kk] + pi*zr[kk] + pr*zi[kk];
+                zr[kk] = nr; zi[kk] = ni;
+            }
+        } else {              // v1 += eta*v7 ; v6 += alfa*v4 ; v7 := v6 + c67*v7  (core.hxx:216-220)
+            float yr[8], yi[8], xr[8], xi[8], br[8], bi[8];
+            #pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                yr[kk] = a.v7[ore + kk*LN]; yi[kk] = a.v7[oim + kk*LN];
+                xr[kk] = a.v1[ore + kk*LN]; xi[kk] = a.v1[oim + kk*LN];
+                br[kk] = a.v4[ore + kk*LN]; bi[kk] = a.v4[oim + kk*LN];
+                zr[kk] = a.v6[ore + kk*LN]; zi[kk] = a.v6[oim + kk*LN];
+            }
+            #pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                xr[kk] = pr*yr[kk] - pi*yi[kk] + xr[kk];
+                xi[kk] = pi*yr[kk] + pr*yi[kk] + xi[kk];
+                float const mr = qr*br[kk] - qi*bi[kk] + zr[kk];
+                float const mi = qi*br[kk] + qr*bi[kk] + zi[kk];
+                zr[kk] = mr; zi[kk] = mi;
+                float const nr = mr + sr*yr[kk] - si*yi[kk];
+                float const ni = mi + si*yr[kk] + sr*yi[kk];
+                yr[kk] = nr; yi[kk] = ni;
+            }
+            #pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                a.v1[ore + kk*LN] = xr[kk]; a.v1[oim + kk*LN] = xi[kk];
+                a.v7[ore + kk*LN] = yr[kk]; a.v7[oim + kk*LN] = yi[kk];
+            }
+        }
+        uint32_t hr[4], lr[4], hi_[4], li_[4];
+        #pragma unroll
+        for (int kk = 0; kk < 8; kk += 2) {
+            a.v6[ore + kk*LN] = zr[kk]; a.v6[oim + kk*LN] = zi[kk];
+            a.v6[ore + (kk + 1)*LN] = zr[kk + 1]; a.v6[oim + (kk + 1)*LN] = zi[kk + 1];
+            vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(zr[kk]), fabsf(zi[kk])), fmaxf(fabsf(zr[kk + 1]), fabsf(zi[kk + 1]))));
+            __half h0, l0, h1, l1;
+            float v0 = zr[kk]*scale, v1 = zr[kk + 1]*scale;
+            h0 = __float2half_rn(v0); l0 = __float2half_rn((v0 - __half2float(h0))*2048.f);
+            h1 = __float2half_rn(v1); l1 = __float2half_rn((v1 - __half2float(h1))*2048.f);
+            hr[kk/2] = xop_pack2(h0, h1); lr[kk/2] = xop_pack2(l0, l1);
+            v0 = zi[kk]*scale; v1 = zi[kk + 1]*scale;
+            h0 = __float2half_rn(v0); l0 = __float2half_rn((v0 - __half2float(h0))*2048.f);
+            h1 = __float2half_rn(v1); l1 = __float2half_rn((v1 - __half2float(h1))*2048.f);
+            hi_[kk/2] = xop_pack2(h0, h1); li_[kk/2] = xop_pack2(l0, l1);
+        }
+        uint4 *dre, *dim_; int lo_off;
+        if (64 == LM) {       // 2 x 2 sub-blocks (k/32, j/32) in the 32 x 32 layout: 8 chunks x 64 rows each
+            int const kh = ko >> 2, q = ko & 3, jh = j >> 5;
+            uint4 *const base = a.xop + (size_t(blk)*4 + kh*2 + jh)*(8*64) + size_t(q)*64;
+            dre = base + (j & 31); dim_ = base + 32 + (j & 31); lo_off = 4*64;
+        } else {
+            uint4 *const base = a.xop + size_t(blk)*(2*KO*2*LN) + size_t(ko)*(2*LN);
+            dre = base + j; dim_ = base + LN + j; lo_off = KO*2*LN;
+        }
+        dre[0] = make_uint4(hr[0], hr[1], hr[2], hr[3]);       dim_[0] = make_uint4(hi_[0], hi_[1], hi_[2], hi_[3]);
+        dre[lo_off] = make_uint4(lr[0], lr[1], lr[2], lr[3]);  dim_[lo_off] = make_uint4(li_[0], li_[1], li_[2], li_[3]);
+    }
+
+    // ---- max|v6| of this column for the next bound: tile maximum, the last tile folds ---------------------------------
+    s_max[tid] = vmax;
+    __syncthreads();
+    for (int half = SUBS >> 1; half > 0; half >>= 1) {
+        if (sub < half) s_max[tid] = fmaxf(s_max[tid], s_max[tid + half*LN]);
+        __syncthreads();
+    }
+    if (0 == sub) a.partmax[size_t(blockIdx.x)*64 + j] = s_max[j];
+    uint32_t const t0 = a.coltile[c], t1 = a.coltile[c + 1];
+    __threadfence();
+    __syncthreads();
+    if (0 == tid) s_last = (atomicAdd(&a.ticket[c], 1u) == (t1 - t0) - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (0 == tid) a.ticket[c] = 0;
+    if (tid < LN) {
+        float m = 0.f;
+        for (uint32_t tt = t0; tt < t1; ++tt) m = fmaxf(m, __ldcg(&a.partmax[size_t(tt)*64 + tid]));
+        a.mx6[size_t(c)*LN + tid] = m;
+    }
+}
+
 // v[bpos[b]] += scal*B[b]  (add_RHS, linalg.hxx:383-404)
 template <typename real_t>
 __global__ void add_rhs_kernel(real_t *__restrict__ v, real_t const *__restrict__ B, real_t scal,
@@ -494,6 +685,13 @@ VecArgs<real_t> make_args(Plan const &p) {
     a.LM = p.LM; a.LN = p.LN;
     int sh = 0; while ((1 << sh) < p.LM) ++sh;
     a.lmShift = sh;
+    a.mx4 = a.mx5 = a.mx6 = a.partmax = a.xs = a.xsinv = nullptr; a.xop = nullptr;
+    if (p.use_tc16) {
+        size_t const n = size_t(p.nCols)*p.LN;
+        a.mx4 = ws<float>(p, p.off_mx); a.mx5 = a.mx4 + n; a.mx6 = a.mx5 + n;
+        a.partmax = ws<float>(p, p.off_xpart); a.xs = ws<float>(p, p.off_xs); a.xsinv = ws<float>(p, p.off_xsinv);
+        a.xop = ws<uint4>(p, p.off_xop);
+    }
     return a;
 }
 
@@ -510,7 +708,11 @@ void launch_one(Plan const &p, cudaStream_t stream) {
         smem = std::max<size_t>(smem, 3*size_t(threads));
         smem *= sizeof(double);
     }
-    vec_kernel<real_t, VEC, OP><<<p.nTiles, threads, smem, stream>>>(make_args<real_t>(p));
+    constexpr bool kWritesV45 = (OP == OP_INIT || OP == OP_E1 || OP == OP_K2 || OP == OP_E2);
+    if (std::is_same<real_t, float>::value && kWritesV45 && p.use_tc16)
+        vec_kernel<real_t, VEC, OP, std::is_same<real_t, float>::value && kWritesV45><<<p.nTiles, threads, smem, stream>>>(make_args<real_t>(p));
+    else
+        vec_kernel<real_t, VEC, OP, false><<<p.nTiles, threads, smem, stream>>>(make_args<real_t>(p));
 }
 
 template <typename real_t, int VEC>
@@ -529,6 +731,24 @@ void launch_op(Plan const &p, int op, cudaStream_t stream) {
 }
 
 } // namespace
+
+// K1 / K3 that also emit the tensor-core product's X operand from the v6 they write (plans with use_tc16 only)
+tfqmrgpuStatus_t launch_vecop_xop(Plan const &p, int op, cudaStream_t stream)
+{
+    if (!p.use_tc16 || (OP_K1 != op && OP_K3 != op)) return TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED);
+    VecArgs<float> const a = make_args<float>(p);
+#define TFQ_VX(LM, LN) case LM*1000 + LN: \
+        if (OP_K1 == op) vec_xop_kernel<OP_K1, LM, LN><<<p.nTiles, 256, 0, stream>>>(a); \
+        else             vec_xop_kernel<OP_K3, LM, LN><<<p.nTiles, 256, 0, stream>>>(a); \
+        break;
+    switch (p.LM*1000 + p.LN) {
+        TFQ_VX(16, 16) TFQ_VX(16, 32) TFQ_VX(16, 64) TFQ_VX(32, 32) TFQ_VX(32, 64) TFQ_VX(64, 64)
+        default: return TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED);
+    }
+#undef TFQ_VX
+    TFQ_CUDA(cudaGetLastError());
+    return TFQMRGPU_STATUS_SUCCESS;
+}
 
 tfqmrgpuStatus_t launch_vecop(Plan const &p, int op, cudaStream_t stream)
 {
