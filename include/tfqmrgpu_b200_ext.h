@@ -90,6 +90,32 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getSolveProfile(tfqmrgpuBsrsvPlan_t plan, doubl
 typedef int32_t (*tfqmrgpuxOperator_t)(void *ctx, void *y, void const *x, int32_t const *state, int32_t expect, cudaStream_t stream);
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_setOperator(tfqmrgpuBsrsvPlan_t plan, tfqmrgpuxOperator_t op, void *ctx);
 
+/* ---- several GPUs: the independent right-hand-side block columns of X/B are sharded, A is replicated --------
+ *
+ * (1) One process, several devices - for C, Fortran and Julia callers.  Call setDevices after createPlan and before
+ *     bufferSize (or set the environment variable TFQMRGPU_NUM_GPUS=N before createPlan: devices 0..N-1).  From then on the
+ *     ordinary entry points (bufferSize, setBuffer, setMatrix, solve, getInfo, getMatrix) drive all devices: the caller's
+ *     single workspace lives on the device that was current at createPlan and holds that device's shard plus the gathered X;
+ *     the other devices' workspaces are allocated by the library.  A is uploaded in nDevices parts over every device's own
+ *     PCIe link and exchanged device to device; the solve keeps the reference's GLOBAL iteration and probe rule
+ *     (core.hxx:239-299) by exchanging three numbers per shard and iteration; X is gathered device to device when
+ *     getMatrix asks for it.  devices == NULL: 0 .. nDevices-1.  nDevices == 1 restores the single-GPU plan. */
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setDevices(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, int nDevices, int const *devices);
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getDevices(tfqmrgpuBsrsvPlan_t plan, int *nDevices, int *devices, int arrayLength);
+
+/* (2) One process per GPU (MPI / torch.distributed callers): every rank creates an ordinary plan for ITS block columns and
+ *     registers an exchange: `slots` is device memory of 2*2*nShards*4 doubles on this rank's GPU; whenever the solver needs
+ *     the other shards' convergence monitors it calls hook(ctx, slots + offset, nShards*4, stream): the hook must all-gather,
+ *     in place and on `stream`, the nShards blocks of 4 doubles starting at the pointer it is given (block `shard` is this
+ *     rank's contribution; NCCL: ncclAllGather(ptr + 4*shard, ptr, 4, ncclDouble, comm, stream)).  nRhsGlobal = number of
+ *     right-hand sides over all shards.  hook == NULL removes the exchange.  tileBlocksHint: blocks per vector tile of the
+ *     UNSHARDED problem (getPlanInfo of a global plan, or 0) - with it a shard reproduces the single-GPU bits of its columns. */
+typedef int32_t (*tfqmrgpuxExchange_t)(void *ctx, double *slots, int count, cudaStream_t stream);
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setShardExchange(tfqmrgpuBsrsvPlan_t plan, int shard, int nShards, int64_t nRhsGlobal,
+    double *slots, tfqmrgpuxExchange_t hook, void *ctx);
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setTileHint(tfqmrgpuBsrsvPlan_t plan, int64_t tileBlocksHint);
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getTileBlocks(tfqmrgpuBsrsvPlan_t plan, int64_t *tileBlocks);
+
 #ifdef __cplusplus
 }
 #endif

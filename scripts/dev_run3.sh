@@ -1,0 +1,11 @@
+set -x
+timeout 900 python tests/tools/dev_tc16_check.py > gpurun_out/tc16_check3.log 2>&1; echo "rc=$?" >> gpurun_out/tc16_check3.log
+grep -E "FAIL|PASS|rc=|Error|error|worst" gpurun_out/tc16_check3.log | head -20
+timeout 300 python tests/tools/dev_tc16_acc.py > gpurun_out/tc16_acc3.log 2>&1
+TFQMRGPU_DEV_SKIP_XOP=1 timeout 300 python scripts/dev_spmm_time.py > gpurun_out/tc16_time3.log 2>&1
+timeout 300 python scripts/dev_spmm_time.py >> gpurun_out/tc16_time3.log 2>&1
+for m in 1 4 7; do TFQMRGPU_DEV_SKIP_XOP=1 TFQMRGPU_LIB=tfqmrgpu_b200/lib/ablate/libtfQMRgpu16_$m.so timeout 300 python scripts/dev_spmm_time.py >> gpurun_out/tc16_time3.log 2>&1; done
+TFQMRGPU_LIB=$PWD/tfqmrgpu_b200/lib/ablate/libtfQMRgpu16_trace.so TFQMRGPU_DEV_SKIP_XOP=1 timeout 300 python scripts/dev_tc16_trace.py > gpurun_out/tc16_trace3.log 2>&1
+cat gpurun_out/tc16_time3.log gpurun_out/tc16_trace3.log gpurun_out/tc16_acc3.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu3.log 2>&1; tail -30 gpurun_out/pytest_gpu3.log
+timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench3.json 2> gpurun_out/bench3.err; tail -c 3000 gpurun_out/bench3.json

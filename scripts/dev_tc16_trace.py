@@ -17,9 +17,10 @@ assert 0 == lib.tfq_tc16_trace_dump(buf.ctypes.data_as(ctypes.c_void_p), buf.siz
 t = buf.reshape(8, 8)
 info = pl.plan_info()
 ne = info['nEntries']/148.
-roles = [('copy warp', ['wait done', 'issue copy']), ('MMA warp', ['wait a/x full', 'issue', 'wait acc free', 'segment setup']),
-         ('converters g0', ['wait done', 'st + arrive', '-', 'loads issue']), ('converters g1', ['wait done', 'st + arrive', '-', 'loads issue']),
-         ('epilogue warp', ['wait acc full', 'tmem ld + sum', 'exchange + store'])]
+roles = [('copy warp', ['wait done', 'issue copy']), ('MMA warp 0', ['wait a/x full', 'issue', 'wait acc free', 'segment setup']),
+         ('MMA warp 1', ['wait a/x full', 'issue', 'wait acc free', 'segment setup']),
+         ('converters hi', ['wait X landed', 'LDS + transform', 'wait stage free', 'st + arrive']), ('converters lo', ['wait X landed', 'LDS + transform', 'wait stage free', 'st + arrive']),
+         ('epilogue warp', ['wait acc full', 'tmem ld + sum', 'store'])]
 for r, (name, laps) in enumerate(roles):
     tot = t[r].sum()
     print(f'{name:14s} total {tot:9d} cycles = {tot/ne:7.1f} per entry of the CTA | ' + ', '.join(f'{l} {t[r, k]/ne:6.1f}' for k, l in enumerate(laps) if l != '-'))

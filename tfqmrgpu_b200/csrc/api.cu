@@ -74,6 +74,17 @@ static tfqmrgpuStatus_t download_vector(Handle *h, Plan &p, size_t off_vec, void
     if (nullptr == p.pBuffer || nullptr == val) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     bool const is_double = ('z' == p.precision);
     if (('z' == lower(precision)) != is_double) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, precision);
+    if (p.multi) {      // several devices: gather the shards' X device to device, convert on the home device
+        if (off_vec != p.off_v[1]) return TFQ_ERR(TFQMRGPU_NO_IMPLEMENTATION);
+        st = multi_gather_x(p, h->stream);
+        if (st) return st;
+        char *const gx = p.pBuffer + multi_off_gx(p), *const scratch = p.pBuffer + multi_off_scratch(p);
+        st = convert_permuted(p, scratch, gx, p.nnzbX, p.LM, p.LN, is_double, layout, trans, scal_imag, false, h->stream);
+        if (st) return st;
+        TFQ_CUDA(cudaMemcpyAsync(val, scratch, p.vecBytes, cudaMemcpyDeviceToHost, h->stream));
+        TFQ_CUDA(cudaStreamSynchronize(h->stream));
+        return TFQMRGPU_STATUS_SUCCESS;
+    }
     // out of place through a scratch vector, so the device copy keeps its solver layout
     // (the reference transposes X in place and leaves it in host layout, tfqmrgpu.cu:552-600)
     size_t const off_scratch = (off_vec == p.off_v[9]) ? p.off_v[8] : p.off_v[9];
@@ -171,6 +182,14 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_createPlan(tfqmrgpuHandle_t handle, tfqmrgpuBsrs
     cudaStream_t const stream = handle ? static_cast<Handle*>(handle)->stream : nullptr;
     tfqmrgpuStatus_t const st = plan_analyse(*p, stream, bsrRowPtrA, bsrColIndA, bsrRowPtrX, bsrColIndX, bsrRowPtrB, bsrColIndB, echo);
     if (TFQMRGPU_STATUS_SUCCESS != st) { plan_release(*p); delete p; return st; }
+    // TFQMRGPU_NUM_GPUS=N: shard the right-hand-side block columns over devices 0..N-1 (same as tfqmrgpux_bsrsv_setDevices)
+    if (char const *e = std::getenv("TFQMRGPU_NUM_GPUS")) {
+        int const ngpu = std::atoi(e);
+        if (ngpu > 1) {
+            tfqmrgpuStatus_t const mst = multi_set_devices(*p, ngpu, nullptr);
+            if (TFQMRGPU_STATUS_SUCCESS != mst) { plan_release(*p); delete p; return mst; }
+        }
+    }
     *plan = reinterpret_cast<tfqmrgpuBsrsvPlan_t>(p);
     return TFQMRGPU_STATUS_SUCCESS;
 }
@@ -199,14 +218,23 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_bufferSize(tfqmrgpuHandle_t handle, tfqmrgpuBsrs
         case 'd': case 'z': prec = 'z'; break;
         default: prec = 'z';
     }
-    p.LM = LM; p.LN = LN; p.precision = prec;
+    // Whatever happens below, a previously registered workspace was laid out for the OLD configuration: forget it first, so
+    // that no later setMatrix/solve can run with a stale layout after a failed re-configuration.
+    p.pBuffer = nullptr; p.bufferBytes = 0; p.v3_ready = false; p.configured = false;
+    plan_drop_graph(p);
     if (nullptr == pBufferSizeInBytes) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     *pBufferSizeInBytes = 0;
     if (!block_size_allowed(LM, LN)) return TFQMRGPU_BLOCKSIZE_MISSING + TFQMRGPU_CODE_CHAR*LM + TFQMRGPU_CODE_LINE*LN; // tfqmrgpu.cu:70
     if ('m' == prec) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, prec);                                             // tfqmrgpu.cu:44
+    if (p.multi) {
+        tfqmrgpuStatus_t const mst = multi_buffer_size(p, LM, LN, prec, pBufferSizeInBytes);
+        if (TFQMRGPU_STATUS_SUCCESS != mst) { p.bufferBytes = 0; *pBufferSizeInBytes = 0; return mst; }
+        p.configured = true;
+        return TFQMRGPU_STATUS_SUCCESS;
+    }
     tfqmrgpuStatus_t const st = plan_configure(p, static_cast<Handle*>(handle)->stream, LM, LN, prec);
-    if (TFQMRGPU_STATUS_SUCCESS != st) return st;
-    p.pBuffer = nullptr; p.v3_ready = false; // a new size invalidates a previously registered buffer
+    if (TFQMRGPU_STATUS_SUCCESS != st) { p.bufferBytes = 0; return st; }
+    p.configured = true;
     *pBufferSizeInBytes = p.bufferBytes;
     return TFQMRGPU_STATUS_SUCCESS;
 }
@@ -216,8 +244,9 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_setBuffer(tfqmrgpuHandle_t handle, tfqmrgpuBsrsv
     if (nullptr == pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     if (nullptr == plan || nullptr == handle) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     Plan &p = *P(plan);
-    if (0 == p.bufferBytes) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR); // bufferSize has not been called
+    if (!p.configured || 0 == p.bufferBytes) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR); // bufferSize has not been called (successfully)
     if (size_t(pBuffer) & 255) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);  // 2^TFQMRGPU_MEMORY_ALIGNMENT
+    if (p.multi) return multi_set_buffer(p, pBuffer);
     cudaStream_t const stream = static_cast<Handle*>(handle)->stream;
     p.pBuffer = static_cast<char*>(pBuffer);
     plan_drop_graph(p);               // the captured iteration body holds pointers into the old workspace
@@ -255,8 +284,10 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_setMatrix(tfqmrgpuHandle_t handle, tfqmrgpuBsrsv
         default: return TFQ_ERRC(TFQMRGPU_VARIABLENAME_UNKNOWN, var);
     }
     if (nnzb < 1) return TFQMRGPU_STATUS_SUCCESS;
-    if (nullptr == p.pBuffer || nullptr == val) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    if (nullptr == p.pBuffer || nullptr == val || !p.configured) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    if ('z' != p.precision && 'c' != p.precision) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, p.precision);
     if (('z' == lower(precision)) != is_double) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, precision); // tfqmrgpu.cu:538-542
+    if (p.multi) return multi_set_matrix(p, v, val, precision, transposition, layout, trans, scal_imag);
     if ('a' == v) {
         char *const dst = p.pBuffer + p.off_A;
         size_t const blockBytes = 2*size_t(p.LM)*p.LM*s, bytes = size_t(nnzb)*blockBytes;
@@ -319,6 +350,10 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_getMatrix(tfqmrgpuHandle_t handle, tfqmrgpuBsrsv
 // ---- solve / getInfo: tfqmrgpu.cu:648-679 -----------------------------------------------------------
 tfqmrgpuStatus_t tfqmrgpu_bsrsv_solve(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, double const threshold, int const maxIterations) {
     if (nullptr == plan || nullptr == handle) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    if (P(plan)->multi) {
+        if (nullptr == P(plan)->pBuffer || !P(plan)->configured) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+        return multi_solve(*P(plan), threshold, maxIterations);
+    }
     return solve(*P(plan), static_cast<Handle*>(handle)->stream, threshold, maxIterations);
 }
 
@@ -459,6 +494,7 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getPlanInfo(tfqmrgpuBsrsvPlan_t plan, int64_t i
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_setV3(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, float const *v3, int onDevice) {
     if (nullptr == plan || nullptr == handle || nullptr == v3) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     Plan &p = *P(plan);
+    if (p.multi) return TFQ_ERR(TFQMRGPU_NO_IMPLEMENTATION);       // (a multi-device plan slices the reference's stream itself)
     if (nullptr == p.pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     cudaStream_t const stream = static_cast<Handle*>(handle)->stream;
     size_t const bytes = size_t(p.nnzbX)*2*p.LM*p.LN*sizeof(float);
@@ -473,6 +509,7 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_setV3(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPla
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_getV3(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, float *v3Host) {
     if (nullptr == plan || nullptr == handle || nullptr == v3Host) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     Plan &p = *P(plan);
+    if (p.multi) return TFQ_ERR(TFQMRGPU_NO_IMPLEMENTATION);
     if (nullptr == p.pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     cudaStream_t const stream = static_cast<Handle*>(handle)->stream;
     float *const scratch = ws<float>(p, p.off_v[9]);
@@ -500,6 +537,7 @@ tfqmrgpuStatus_t tfqmrgpux_randomShadow(tfqmrgpuHandle_t handle, float *devOut, 
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_setOperator(tfqmrgpuBsrsvPlan_t plan, tfqmrgpuxOperator_t op, void *ctx) {
     if (nullptr == plan) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     Plan &p = *P(plan);
+    if (p.multi) return TFQ_ERR(TFQMRGPU_NO_IMPLEMENTATION);
     p.user_op = op; p.user_ctx = op ? ctx : nullptr;
     plan_drop_graph(p);          // a captured iteration body holds the built-in product
     return TFQMRGPU_STATUS_SUCCESS;
@@ -508,6 +546,7 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_setOperator(tfqmrgpuBsrsvPlan_t plan, tfqmrgpux
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_multiply(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, int nrep) {
     if (nullptr == plan || nullptr == handle) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     Plan &p = *P(plan);
+    if (p.multi) return TFQ_ERR(TFQMRGPU_NO_IMPLEMENTATION);
     if (nullptr == p.pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     for (int r = 0; r < nrep; ++r) {
         tfqmrgpuStatus_t const st = launch_spmm(p, p.pBuffer + p.off_v[9], p.pBuffer + p.off_v[1], -1, static_cast<Handle*>(handle)->stream);
@@ -532,6 +571,7 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getVector(tfqmrgpuHandle_t handle, tfqmrgpuBsrs
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_getWindow(tfqmrgpuBsrsvPlan_t plan, char var, size_t *offset, size_t *length) {
     if (nullptr == plan || nullptr == offset || nullptr == length) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     Plan const &p = *P(plan);
+    if (p.multi) return TFQ_ERR(TFQMRGPU_NO_IMPLEMENTATION);
     size_t const s = ('z' == p.precision) ? 8 : 4;
     switch (lower(var)) {
         case 'x': *offset = p.off_v[1]; *length = p.vecBytes; break;
@@ -546,6 +586,7 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getWindow(tfqmrgpuBsrsvPlan_t plan, char var, s
 
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_getRhsStatus(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, int8_t *statusHost) {
     if (nullptr == plan || nullptr == handle || nullptr == statusHost) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    if (P(plan)->multi) return (nullptr == P(plan)->pBuffer) ? TFQ_ERR(TFQMRGPU_POINTER_INVALID) : multi_rhs_status(*P(plan), statusHost);
     Plan const &p = *P(plan);
     if (nullptr == p.pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     cudaStream_t const stream = static_cast<Handle*>(handle)->stream;
@@ -561,6 +602,42 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getSolveStats(tfqmrgpuBsrsvPlan_t plan, double 
     Plan const &p = *P(plan);
     stats[0] = p.stat_probes; stats[1] = p.stat_launches; stats[2] = p.stat_bodies; stats[3] = p.stat_ms;
     stats[4] = p.stat_bound2; stats[5] = p.stat_target2; stats[6] = 0; stats[7] = 0;
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+// ---- several GPUs (tfqmrgpu_b200_ext.h) ------------------------------------------------------------------
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setDevices(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, int nDevices, int const *devices) {
+    if (nullptr == plan || nullptr == handle) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    if (nDevices < 1 || nDevices > kMaxDevices) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+    tfqmrgpuStatus_t const st = multi_set_devices(*P(plan), nDevices, devices);
+    if (TFQMRGPU_STATUS_SUCCESS != st) multi_destroy(*P(plan));
+    return st;
+}
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getDevices(tfqmrgpuBsrsvPlan_t plan, int *nDevices, int *devices, int arrayLength) {
+    if (nullptr == plan || nullptr == nDevices) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    *nDevices = multi_get_devices(*P(plan), devices, arrayLength);
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setShardExchange(tfqmrgpuBsrsvPlan_t plan, int shard, int nShards, int64_t nRhsGlobal,
+    double *slots, tfqmrgpuxExchange_t hook, void *ctx) {
+    if (nullptr == plan) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan &p = *P(plan);
+    if (p.multi) return TFQ_ERR(TFQMRGPU_NO_IMPLEMENTATION);
+    plan_drop_graph(p);              // the captured iteration body decides alone
+    if (nullptr == hook || nShards <= 1) { p.exch = Exchange(); return TFQMRGPU_STATUS_SUCCESS; }
+    if (nullptr == slots || shard < 0 || shard >= nShards) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    p.exch.nshards = nShards; p.exch.shard = shard; p.exch.nrhs_global = nRhsGlobal; p.exch.slots = slots;
+    p.exch.hook = hook; p.exch.hook_ctx = ctx; p.exch.parity = 0;
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setTileHint(tfqmrgpuBsrsvPlan_t plan, int64_t tileBlocksHint) {
+    if (nullptr == plan) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    P(plan)->tile_blocks_hint = (tileBlocksHint > 0) ? size_t(tileBlocksHint) : 0;     // takes effect with the next bufferSize
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getTileBlocks(tfqmrgpuBsrsvPlan_t plan, int64_t *tileBlocks) {
+    if (nullptr == plan || nullptr == tileBlocks) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    *tileBlocks = int64_t(P(plan)->tile_blocks);
     return TFQMRGPU_STATUS_SUCCESS;
 }
 

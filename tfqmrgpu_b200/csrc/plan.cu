@@ -225,6 +225,11 @@ tfqmrgpuStatus_t plan_analyse(Plan &p, cudaStream_t stream,
     p.h_rowptrX.resize(mb + 1);
     p.maxColsPerRow = 1;
     for (int r = 0; r <= mb; ++r) p.h_rowptrX[r] = rpX[r] - off;
+    p.h_rpA.resize(mb + 1); p.h_rpB.resize(mb + 1);
+    for (int r = 0; r <= mb; ++r) { p.h_rpA[r] = rpA[r] - off; p.h_rpB[r] = rpB[r] - off; }
+    p.h_ciA.resize(nnzbA); for (int i = 0; i < nnzbA; ++i) p.h_ciA[i] = ciA[i] - off;
+    p.h_ciX.assign(ciX, ciX + nnzbX);                 // X and B column values are labels, compared unshifted (tfqmrgpu.cu:238-241)
+    p.h_ciB.assign(ciB, ciB + nnzbB);
     for (int r = 0; r < mb; ++r) p.maxColsPerRow = std::max(p.maxColsPerRow, p.h_rowptrX[r + 1] - p.h_rowptrX[r]);
 
     // ---- upload the six index arrays --------------------------------------------------------------
@@ -365,6 +370,7 @@ static void free_configured(Plan &p) {
 }
 
 void plan_release(Plan &p) {
+    multi_destroy(p);
     free_configured(p);
     cudaFree(p.d_starts); cudaFree(p.d_pairs); cudaFree(p.d_subset); cudaFree(p.d_colindx);
     cudaFree(p.d_perm); cudaFree(p.d_iperm); cudaFree(p.d_bpos); cudaFree(p.d_blockcol); cudaFree(p.d_rowptrA);
@@ -376,9 +382,23 @@ void plan_release(Plan &p) {
     for (auto &e : p.chunk_ev) if (e) cudaEventDestroy(e);
 }
 
+// X blocks per vector tile: 16 KiB of a vector per tile, 4 KiB when that would leave SMs without a tile (FD_problem.xml, 175 KB
+// per vector: 2.98 -> 2.64 ms per solve; on the 1728-row sweep 16 KiB is the better one); at least nnzbX / (4 tiles per SM)
+size_t plan_tile_blocks(size_t nnzbX, size_t blockBytes, int nsm)
+{
+    size_t const target = size_t(nsm)*4;
+    size_t tb = std::max<size_t>(1, (nnzbX + target - 1)/target);
+    char const *env_tile = std::getenv("TFQMRGPU_TILE_KB");      // dev switch: minimum bytes of one vector per tile
+    size_t const vec_bytes = nnzbX*blockBytes;
+    size_t const tile_kb = env_tile ? size_t(std::max(1, std::atoi(env_tile))) : ((vec_bytes/(16*1024) < size_t(nsm)) ? 4 : 16);
+    size_t const tb_min = std::max<size_t>(1, (tile_kb*1024 + blockBytes - 1)/blockBytes);
+    return std::max(tb, tb_min);
+}
+
 tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, char precision)
 {
     free_configured(p);
+    p.configured = false;
     p.LM = LM; p.LN = LN; p.precision = precision;
     bool const is_double = ('z' == precision);
     size_t const s = is_double ? 8 : 4;
@@ -391,15 +411,9 @@ tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, ch
 
     // ---- vector tiles: every tile is a contiguous range of blocks of ONE block column ---------------
     {
-        size_t const target = size_t(nsm)*4;
-        size_t tb = std::max<size_t>(1, (size_t(p.nnzbX) + target - 1)/target);
-        char const *env_tile = std::getenv("TFQMRGPU_TILE_KB");      // dev switch: minimum bytes of one vector per tile
-        // 16 KiB of a vector per tile, 4 KiB when that would leave SMs without a tile (FD_problem.xml, 175 KB per vector:
-        // 2.98 -> 2.64 ms per solve; on the 1728-row sweep 16 KiB is the better one)
-        size_t const vec_bytes = size_t(p.nnzbX)*blockBytes;
-        size_t const tile_kb = env_tile ? size_t(std::max(1, std::atoi(env_tile))) : ((vec_bytes/(16*1024) < size_t(nsm)) ? 4 : 16);
-        size_t const tb_min = std::max<size_t>(1, (tile_kb*1024 + blockBytes - 1)/blockBytes);
-        tb = std::max(tb, tb_min);
+        size_t tb = plan_tile_blocks(size_t(p.nnzbX), blockBytes, nsm);
+        if (p.tile_blocks_hint > 0) tb = p.tile_blocks_hint;          // a shard tiles its columns like the unsharded plan does
+        p.tile_blocks = tb;
         std::vector<Tile> tiles;
         std::vector<uint32_t> coltile(size_t(nb) + 1, 0);
         for (uint32_t c = 0; c < nb; ++c) {
@@ -509,9 +523,17 @@ tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, ch
             TFQ_CUDA(cudaMemcpyAsync(p.d_cta_u0, cta_u0.data(), cta_u0.size()*4, cudaMemcpyHostToDevice, stream));
             TFQ_CUDA(cudaMemcpyAsync(p.d_unit_row, urow.data(), urow.size()*4, cudaMemcpyHostToDevice, stream));
             TFQ_CUDA(cudaStreamSynchronize(stream));             // the host vectors are locals
+            // Which form of the product: the planar one (four real products, spmm_tc16p.cu) is the fast one, but its error on sums that
+            // cancel between the real products grows with the row length (measured ~8e-8 * entries * LM on the reference harness's cos/sin
+            // fill, whose pass bar is 1e-4 absolute): plans whose longest row has entries * LM <= 864 (the 27-point stencil of 32 x 32
+            // blocks: 7e-5) use it, longer rows the direct form (spmm_tc16.cu, ~1e-5 on the same operands).
+            uint32_t max_entries = 0;
+            for (uint32_t u = 0; u < p.nUnits; ++u) max_entries = std::max(max_entries, cnt[u]);
+            char const *env_form = std::getenv("TFQMRGPU_TC_FORM");
+            p.tc_planar = env_form ? ('p' == env_form[0]) : (uint64_t(max_entries)*uint64_t(LM) <= 864);
             char const *env_seg = std::getenv("TFQMRGPU_TC_CHAIN");   // entries per accumulation segment
             int const seg_env = env_seg ? std::atoi(env_seg) : 0;
-            p.tc_seg = (seg_env > 0) ? seg_env : spmm_tc16_default_segment(std::min(LM, 32));
+            p.tc_seg = (seg_env > 0) ? seg_env : (p.tc_planar ? spmm_tc16p_default_segment(std::min(LM, 32)) : spmm_tc16_default_segment(std::min(LM, 32)));
         } else {
             TFQ_CUDA(exclusive_scan(p.d_unit_e0, d_cnt.ptr, first.size() + 1, stream));
         }

@@ -13,8 +13,38 @@
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <dlfcn.h>
 
 namespace tfq {
+
+// The reference brackets its solver with the NVTX ranges "tfQMR preparation" and "tfQMR iterations" (tfqmrgpu.hxx:6-27,
+// core.hxx:29,177).  NVTX is resolved at run time (libnvToolsExt.so.1, only if TFQMRGPU_NVTX=1 asks for it), so the library
+// has no link dependency on it and the ranges cost nothing when switched off.
+namespace {
+struct NvtxApi { int (*push)(char const*) = nullptr; int (*pop)() = nullptr; bool tried = false; };
+NvtxApi &nvtx() {
+    static NvtxApi api;
+    if (!api.tried) {
+        api.tried = true;
+        char const *e = std::getenv("TFQMRGPU_NVTX");
+        if (e && '0' != e[0]) {
+            void *lib = dlopen("libnvToolsExt.so.1", RTLD_NOW | RTLD_GLOBAL);
+            if (nullptr == lib) lib = dlopen("libnvToolsExt.so", RTLD_NOW | RTLD_GLOBAL);
+            if (lib) {
+                api.push = reinterpret_cast<int (*)(char const*)>(dlsym(lib, "nvtxRangePushA"));
+                api.pop  = reinterpret_cast<int (*)()>(dlsym(lib, "nvtxRangePop"));
+            }
+        }
+    }
+    return api;
+}
+struct TfqRange {
+    mutable bool open = false;
+    explicit TfqRange(char const *name) { NvtxApi &n = nvtx(); if (n.push && n.pop) { n.push(name); open = true; } }
+    void end() const { if (open) { nvtx().pop(); open = false; } }
+    ~TfqRange() { end(); }
+};
+} // namespace
 
 namespace {
 constexpr int kAhead = 3;      // iteration bodies the host may run ahead of the last control read-back
@@ -23,13 +53,13 @@ constexpr int kRing = 6;       // read-back slots; slot 6 = final state, slot 7 
 
 namespace {
 constexpr int kBodyKernels = 11;
+}
 
-// one tfQMR iteration (core.hxx:189-233) followed by the residual probe (core.hxx:263-304); every kernel checks the
-// device-resident state first: the iteration kernels run only in state RUN, the probe kernels only in state PROBE
+// one tfQMR iteration (core.hxx:189-233); every kernel checks the device-resident state first and runs only in state RUN
 // (events: nullptr, or four events recorded around the two A*v6 products when profiling)
-tfqmrgpuStatus_t enqueue_body(Plan &p, cudaStream_t stream, cudaEvent_t const *events)
+tfqmrgpuStatus_t enqueue_iteration(Plan &p, cudaStream_t stream, cudaEvent_t const *events)
 {
-    void *const v1 = p.pBuffer + p.off_v[1], *const v6 = p.pBuffer + p.off_v[6];
+    void *const v6 = p.pBuffer + p.off_v[6];
     void *const v8 = p.pBuffer + p.off_v[8], *const v9 = p.pBuffer + p.off_v[9];
     tfqmrgpuStatus_t st;
 #define TFQ_DO(call) do { st = (call); if (TFQMRGPU_STATUS_SUCCESS != st) return st; } while (0)
@@ -50,11 +80,44 @@ tfqmrgpuStatus_t enqueue_body(Plan &p, cudaStream_t stream, cudaEvent_t const *e
     if (events) TFQ_CUDA(cudaEventRecord(events[3], stream));
     TFQ_DO(launch_vecop(p, OP_E2, stream));
     TFQ_DO(launch_vecop(p, OP_K4, stream));
+#undef TFQ_DO
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+// the residual probe (core.hxx:263-304); its kernels run only in state PROBE
+tfqmrgpuStatus_t enqueue_probe(Plan &p, cudaStream_t stream)
+{
+    void *const v1 = p.pBuffer + p.off_v[1], *const v9 = p.pBuffer + p.off_v[9];
+    tfqmrgpuStatus_t st;
+#define TFQ_DO(call) do { st = (call); if (TFQMRGPU_STATUS_SUCCESS != st) return st; } while (0)
     TFQ_DO(launch_spmm(p, v9, v1, STATE_PROBE, stream));               // v9 := A*v1     (core.hxx:265)
     TFQ_DO(launch_add_rhs(p, v9, -1.0, STATE_PROBE, stream));          // v9 -= b        (core.hxx:267)
     TFQ_DO(launch_vecop(p, OP_N3, stream));
 #undef TFQ_DO
     return TFQMRGPU_STATUS_SUCCESS;
+}
+
+namespace {
+
+// all shards' convergence monitors of (kind, parity) to every shard, then the common decision (multi-process runs: the hook
+// all-gathers on the solver's stream; one process with several devices exchanges through multi.cu instead)
+tfqmrgpuStatus_t exchange_and_decide(Plan &p, int kind, cudaStream_t stream)
+{
+    if (p.exch.hook) {
+        int32_t const hst = p.exch.hook(p.exch.hook_ctx, exchange_slots(p, kind), 4*p.exch.nshards, stream);
+        if (hst) return tfqmrgpuStatus_t(hst);
+    }
+    return launch_decide(p, kind, stream);
+}
+
+// iteration followed by the probe; with an exchange registered, the shards' monitors are combined after K4 and after N3
+tfqmrgpuStatus_t enqueue_body(Plan &p, cudaStream_t stream, cudaEvent_t const *events)
+{
+    tfqmrgpuStatus_t st = enqueue_iteration(p, stream, events);
+    if (TFQMRGPU_STATUS_SUCCESS == st && p.exch.slots) st = exchange_and_decide(p, 0, stream);
+    if (TFQMRGPU_STATUS_SUCCESS == st) st = enqueue_probe(p, stream);
+    if (TFQMRGPU_STATUS_SUCCESS == st && p.exch.slots) st = exchange_and_decide(p, 1, stream);
+    return st;
 }
 
 // capture the body once into a CUDA graph: one launch per iteration instead of eleven (small systems such as the
@@ -85,34 +148,18 @@ bool graphs_enabled() {
 }
 } // namespace
 
-tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIterations)
+tfqmrgpuStatus_t solve_begin(Plan &p, cudaStream_t stream, double tolerance, int maxIterations)
 {
-    auto const t_start = std::chrono::steady_clock::now();
     // block size / precision dispatch of the reference (tfqmrgpu.cu:40-72)
     if (!block_size_allowed(p.LM, p.LN))
         return TFQMRGPU_BLOCKSIZE_MISSING + TFQMRGPU_CODE_CHAR*p.LM + TFQMRGPU_CODE_LINE*p.LN;
     if ('z' != p.precision && 'c' != p.precision) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, p.precision);
-    if (nullptr == p.pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    if (nullptr == p.pBuffer || !p.configured) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
 
-    if (nullptr == p.h_ctl) {
-        TFQ_CUDA(cudaMallocHost((void**)&p.h_ctl, 8*sizeof(Control)));
-        for (auto &e : p.ev) TFQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
+    // lazily created host-side resources; every step is retried by the next solve if it fails here
+    for (auto &e : p.ev) if (nullptr == e) TFQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (nullptr == p.h_ctl) TFQ_CUDA(cudaMallocHost((void**)&p.h_ctl, 8*sizeof(Control)));
     Control *const d_ctl = ws<Control>(p, p.off_ctl);
-    double launches = 0;
-    // profiling: CUDA events on the solver's own stream around the solve and around every A*v6 product
-    constexpr int kProfBodies = 256;
-    if (p.profile && p.prof_ev.empty()) {
-        p.prof_ev.resize(2 + 4*kProfBodies, nullptr);
-        for (auto &e : p.prof_ev) TFQ_CUDA(cudaEventCreate(&e));
-    }
-    auto mark = [&](int which) { return p.profile ? cudaEventRecord(p.prof_ev[which], stream) : cudaSuccess; };
-    TFQ_CUDA(mark(0));
-    bool const use_graph = graphs_enabled() && !p.profile && maxIterations > 0 && nullptr == p.user_op;   // (a callback cannot be captured blindly)
-    if (use_graph && nullptr == p.body_exec) {
-        tfqmrgpuStatus_t const gst = build_body_graph(p);
-        if (TFQMRGPU_STATUS_SUCCESS != gst) return gst;
-    }
 
     // ---- initial state (core.hxx:114-131,170-174) ----------------------------------------------------
     Control &c0 = p.h_ctl[7];
@@ -129,11 +176,51 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
     // v1 and v4..v9 are contiguous: the initial guess is discarded like in the reference (core.hxx:125)
     TFQ_CUDA(cudaMemsetAsync(p.pBuffer + p.off_v[1], 0, (p.off_v[9] + p.vecBytes) - p.off_v[1], stream));
     if (p.use_tc16) TFQ_CUDA(cudaMemsetAsync(p.pBuffer + p.off_mx, 0, 3*size_t(p.nCols)*p.LN*sizeof(float), stream));   // max|v6| = 0
+    p.exch.parity = 0;
 
     tfqmrgpuStatus_t st;
-#define TFQ_DO(call) do { st = (call); if (TFQMRGPU_STATUS_SUCCESS != st) return st; launches += 1; } while (0)
-    TFQ_DO(launch_add_rhs(p, p.pBuffer + p.off_v[5], 1.0, -1, stream));    // v5 := b        (core.hxx:153)
-    TFQ_DO(launch_vecop(p, OP_INIT, stream));                              // tau, 1/|b|^2, first dec35
+    st = launch_add_rhs(p, p.pBuffer + p.off_v[5], 1.0, -1, stream);       // v5 := b        (core.hxx:153)
+    if (TFQMRGPU_STATUS_SUCCESS != st) return st;
+    return launch_vecop(p, OP_INIT, stream);                               // tau, 1/|b|^2, first dec35
+}
+
+tfqmrgpuStatus_t solve_finish(Plan &p, Control const &fin, int bodies, double launches)
+{
+    // ---- bookkeeping (core.hxx:133-138,324-325; flop formula of SURVEY.md a14) ------------------------
+    double const N = double(p.nnzbX)*p.LM*p.LN;
+    double const M = double(p.nPairs)*8.*p.LM*p.LM*p.LN;
+    p.flops_performed = fin.iteration*(104.*N + 2.*M) + 4.*N + fin.probes*(M + 4.*N);
+    p.flops_performed_all += p.flops_performed; // the reference never accumulates this (defect, fixed)
+    p.residuum_reached = std::sqrt(fin.residual2_reached);
+    p.iterations_needed = fin.iterations_needed;
+    p.solved = true;
+    p.stat_probes = fin.probes; p.stat_launches = launches; p.stat_bodies = bodies;
+    p.stat_bound2 = fin.max_bound2; p.stat_target2 = fin.target_bound2;
+    return fin.result;
+}
+
+tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIterations)
+{
+    auto const t_start = std::chrono::steady_clock::now();
+    TfqRange const range_prep("tfQMR preparation");     // the reference's NVTX ranges (core.hxx:29,177), behind TFQMRGPU_NVTX=1
+    tfqmrgpuStatus_t st = solve_begin(p, stream, tolerance, maxIterations);
+    if (TFQMRGPU_STATUS_SUCCESS != st) return st;
+    Control *const d_ctl = ws<Control>(p, p.off_ctl);
+    double launches = 2;
+    // profiling: CUDA events on the solver's own stream around the solve and around every A*v6 product
+    constexpr int kProfBodies = 256;
+    if (p.profile && p.prof_ev.empty()) p.prof_ev.resize(2 + 4*kProfBodies, nullptr);
+    if (p.profile) {
+        for (auto &e : p.prof_ev) if (nullptr == e) TFQ_CUDA(cudaEventCreate(&e));
+    }
+    auto mark = [&](int which) { return p.profile ? cudaEventRecord(p.prof_ev[which], stream) : cudaSuccess; };
+    TFQ_CUDA(mark(0));
+    // (a callback cannot be captured blindly; the exchange hook of a sharded run is a host call per iteration)
+    bool const use_graph = graphs_enabled() && !p.profile && maxIterations > 0 && nullptr == p.user_op && nullptr == p.exch.slots;
+    if (use_graph && nullptr == p.body_exec) {
+        tfqmrgpuStatus_t const gst = build_body_graph(p);
+        if (TFQMRGPU_STATUS_SUCCESS != gst) return gst;
+    }
 
     if (verbosity() > 0) { // the reference prints this line unconditionally (core.hxx:167)
         std::vector<double> inv(size_t(p.nCols)*p.LN);
@@ -143,6 +230,8 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
         for (double v : inv) { double const n2 = 1./v; mn = std::min(mn, n2); mx = std::max(mx, n2); }
         std::printf("# norms of B within [%g, %g]\n", std::sqrt(mn), std::sqrt(mx));
     }
+    range_prep.end();
+    TfqRange const range_iter("tfQMR iterations");
 
     int bodies = 0;
     for (int i = 0; i < maxIterations; ++i) {
@@ -156,6 +245,7 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
             launches += kBodyKernels;
         } else {
             bool const prof = p.profile && (i < kProfBodies);
+            p.exch.parity = i & 1;
             st = enqueue_body(p, stream, prof ? &p.prof_ev[2 + 4*i] : nullptr);
             if (TFQMRGPU_STATUS_SUCCESS != st) return st;
             launches += kBodyKernels;
@@ -165,7 +255,6 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
         TFQ_CUDA(cudaEventRecord(p.ev[slot], stream));
         ++bodies;
     }
-#undef TFQ_DO
     Control &fin = p.h_ctl[6];
     TFQ_CUDA(cudaMemcpyAsync(&fin, d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, stream));
     TFQ_CUDA(mark(1));
@@ -183,22 +272,12 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
             }
         }
     }
-
-    // ---- bookkeeping (core.hxx:133-138,324-325; flop formula of SURVEY.md a14) ------------------------
-    double const N = double(p.nnzbX)*p.LM*p.LN;
-    double const M = double(p.nPairs)*8.*p.LM*p.LM*p.LN;
-    p.flops_performed = fin.iteration*(104.*N + 2.*M) + 4.*N + fin.probes*(M + 4.*N);
-    p.flops_performed_all += p.flops_performed; // the reference never accumulates this (defect, fixed)
-    p.residuum_reached = std::sqrt(fin.residual2_reached);
-    p.iterations_needed = fin.iterations_needed;
-    p.solved = true;
-    p.stat_probes = fin.probes; p.stat_launches = launches; p.stat_bodies = bodies;
-    p.stat_bound2 = fin.max_bound2; p.stat_target2 = fin.target_bound2;
+    tfqmrgpuStatus_t const result = solve_finish(p, fin, bodies, launches);
     p.stat_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
     if (verbosity() > 1)
         std::printf("# tfQMRgpu(B200): %d iterations, %d probes, residual %.3e, status %d, %.3f ms\n",
                     fin.iteration, fin.probes, p.residuum_reached, fin.result, p.stat_ms);
-    return fin.result;
+    return result;
 }
 
 } // namespace tfq

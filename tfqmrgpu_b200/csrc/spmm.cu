@@ -485,7 +485,7 @@ tfqmrgpuStatus_t launch_sized(Plan const &p, void *y, void const *x, int expect,
 
 tfqmrgpuStatus_t launch_spmm_operand_ready(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream)
 {
-    if (p.use_tc16 && nullptr == p.user_op) return launch_spmm_tc16(p, y, expect, stream);
+    if (p.use_tc16 && nullptr == p.user_op) return p.tc_planar ? launch_spmm_tc16p(p, y, expect, stream) : launch_spmm_tc16(p, y, expect, stream);
     return launch_spmm(p, y, x, expect, stream);
 }
 
@@ -498,7 +498,7 @@ tfqmrgpuStatus_t launch_spmm(Plan const &p, void *y, void const *x, int expect, 
     if (p.use_tc16) {            // X operand once per product (scales + half pairs, xop.cu), then the tcgen05 product
         static bool const skip_xop = (nullptr != std::getenv("TFQMRGPU_DEV_SKIP_XOP"));   // dev-only: time the product kernel alone
         tfqmrgpuStatus_t const st = skip_xop ? TFQMRGPU_STATUS_SUCCESS : launch_xop(p, x, expect, stream);
-        return st ? st : launch_spmm_tc16(p, y, expect, stream);
+        return st ? st : (p.tc_planar ? launch_spmm_tc16p(p, y, expect, stream) : launch_spmm_tc16(p, y, expect, stream));
     }
     if (p.use_tc) return launch_spmm_tc(p, y, x, expect, stream);
     if (p.use_dmma) return launch_spmm_dmma(p, y, x, expect, stream);

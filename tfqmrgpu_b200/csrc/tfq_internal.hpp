@@ -48,6 +48,17 @@ struct Control {
 
 struct Handle { cudaStream_t stream = nullptr; };
 
+// Column-sharded runs (several GPUs, each solving a range of the right-hand-side block columns): the per-iteration exchange of
+// the convergence monitors that keeps the reference's GLOBAL iteration / probe rule (vecops.cu: decide_kernel).
+struct Exchange {
+    int nshards = 1, shard = 0;
+    long long nrhs_global = 0;
+    double *slots = nullptr;          // device-accessible [2 kinds][2 parities][nshards][4] doubles; nullptr: a single GPU decides alone
+    int parity = 0;                   // of the iteration body being enqueued
+    tfqmrgpuxExchange_t hook = nullptr;   // multi-process runs: all-gathers the slots of (kind, parity) on the solver's stream
+    void *hook_ctx = nullptr;
+};
+
 // one tile of the column-sorted vectors: blocks [b0, b1) all belong to block column `col`
 struct Tile { uint32_t col, b0, b1, pad; };
 
@@ -72,14 +83,21 @@ struct Plan {
     int32_t  *d_rowptrA = nullptr;    // zero-based copy of bsrRowPtrA (row scales of the A operand)
     std::vector<uint32_t> h_colstart; // [nCols+1] first storage block of every block column
     std::vector<int32_t>  h_rowptrX;  // zero-based copy of bsrRowPtrX
+    // zero-based copies of the other index arrays (row ranges of A for chunked / multi-device uploads; sub-plans of column shards)
+    std::vector<int32_t>  h_rpA, h_ciA, h_ciX, h_rpB, h_ciB;
     // block-size dependent: vector tiles
     Tile     *d_tiles = nullptr;      uint32_t nTiles = 0;
     uint32_t *d_coltile = nullptr;    // [nCols+1] first tile of every block column
     // block-size dependent: SpMM units (one CTA each): a block row times <= gmax block columns
     uint32_t nUnits = 0, gmax = 1; uint64_t nEntries = 0;
     bool use_tc16 = false;            // block-sparse product on the tensor cores, fp16 operand pairs (spmm_tc16.cu, xop.cu)
+    bool tc_planar = false;           // ... in the planar form (spmm_tc16p.cu: four real products, the fast kernel for short rows)
     bool use_tc = false;              // the earlier 3xTF32 tensor-core product (spmm_tc.cu; TFQMRGPU_TENSOR=2)
     bool use_dmma = false;            // complex fp64 product on the FP64 tensor pipe (spmm_dmma.cu)
+    Exchange exch;
+    struct MultiPlan *multi = nullptr;       // in-process multi-GPU plan (multi.cu): this Plan is then only the global analysis
+    size_t tile_blocks = 0;                  // X blocks per vector tile chosen by plan_configure
+    size_t tile_blocks_hint = 0;             // shards tile their vectors like the unsharded plan (same reduction order, same bits)
     tfqmrgpuxOperator_t user_op = nullptr;   // user-defined operator instead of the block-sparse product (ext header)
     void *user_ctx = nullptr;
     bool use_small = false;           // LM <= 8: register-staged batches of entries instead of the bulk-copy ring (spmm.cu)
@@ -111,6 +129,7 @@ struct Plan {
     Control *h_ctl = nullptr;         // pinned ring for control read-backs
     cudaEvent_t ev[8] = {nullptr};
     bool v3_ready = false, solved = false;
+    bool configured = false;          // bufferSize succeeded: tiles, units and workspace offsets match LM, LN, precision
     // one tfQMR iteration body (8 iteration kernels + 3 probe kernels) as an instantiated CUDA graph; rebuilt when the
     // workspace or the block configuration changes
     cudaGraphExec_t body_exec = nullptr;
@@ -135,6 +154,20 @@ tfqmrgpuStatus_t plan_analyse(Plan &p, cudaStream_t stream,
 tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, char precision); // tiles, units, offsets
 void plan_release(Plan &p);
 void plan_drop_graph(Plan &p);   // forget the captured iteration body
+size_t plan_tile_blocks(size_t nnzbX, size_t blockBytes, int nsm);   // X blocks per vector tile that plan_configure chooses
+
+// ---- several devices in one process (multi.cu) ---------------------------------------------------------
+tfqmrgpuStatus_t multi_set_devices(Plan &p, int nDevices, int const *devices);
+int  multi_get_devices(Plan const &p, int *devices, int arrayLength);
+void multi_destroy(Plan &p);
+tfqmrgpuStatus_t multi_buffer_size(Plan &p, int LM, int LN, char prec, size_t *bytes);
+tfqmrgpuStatus_t multi_set_buffer(Plan &p, void *pBuffer);
+tfqmrgpuStatus_t multi_set_matrix(Plan &p, char v, void const *val, char precision, char transposition, tfqmrgpuDataLayout_t layout, bool trans, double scal_imag);
+tfqmrgpuStatus_t multi_solve(Plan &p, double tolerance, int maxIterations);
+tfqmrgpuStatus_t multi_gather_x(Plan &p, cudaStream_t homeStream);
+size_t multi_off_gx(Plan const &p);
+size_t multi_off_scratch(Plan const &p);
+tfqmrgpuStatus_t multi_rhs_status(Plan &p, int8_t *statusHost);
 
 // ---- kernels' host launchers --------------------------------------------------------------------
 // block-sparse product y = A*x on storage-ordered vectors; gate: run only if ctl->state == expect (expect < 0: always)
@@ -148,11 +181,14 @@ bool spmm_tc16_supported(int LM, int LN, char precision, int level);
 int  spmm_tc16_columns_per_unit(int LM, int LN);
 int  spmm_tc16_default_segment(int LM);
 tfqmrgpuStatus_t launch_spmm_tc16(Plan const &p, void *y, int expect, cudaStream_t stream);
+int  spmm_tc16p_default_segment(int LM);
+tfqmrgpuStatus_t launch_spmm_tc16p(Plan const &p, void *y, int expect, cudaStream_t stream);   // planar form
 // y = A*x where the X operand of x already exists (written by launch_vecop_xop)
 tfqmrgpuStatus_t launch_spmm_operand_ready(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream);
 tfqmrgpuStatus_t launch_xop(Plan const &p, void const *x, int expect, cudaStream_t stream);          // X operand from a vector
 tfqmrgpuStatus_t launch_aop_blockmax(Plan const &p, uint32_t b0, uint32_t nb, cudaStream_t stream);  // per uploaded chunk of A
 tfqmrgpuStatus_t launch_aop_convert(Plan const &p, cudaStream_t stream);                            // after the last chunk
+tfqmrgpuStatus_t launch_aop_convert_rows(Plan const &p, int row0, int row1, cudaStream_t stream);    // the same for a range of block rows
 // DMMA variant (spmm_dmma.cu): complex fp64, LM and LN in {16, 32, 64}; also switched off by TFQMRGPU_TENSOR=0
 bool spmm_dmma_supported(int LM, int LN, char precision);
 int  spmm_dmma_columns_per_unit(int LM, int LN);
@@ -160,6 +196,8 @@ tfqmrgpuStatus_t launch_spmm_dmma(Plan const &p, void *y, void const *x, int exp
 // fused vector algebra, see vecops.cu
 enum VecOp : int { OP_INIT = 0, OP_K1, OP_E1, OP_K2, OP_K3, OP_E2, OP_K4, OP_N3, OP_COUNT };
 tfqmrgpuStatus_t launch_vecop(Plan const &p, int op, cudaStream_t stream);
+inline double* exchange_slots(Plan const &p, int kind) { return p.exch.slots + size_t((kind*2 + p.exch.parity)*p.exch.nshards)*4; }
+tfqmrgpuStatus_t launch_decide(Plan const &p, int kind, cudaStream_t stream);
 // OP_K1 / OP_K3 that also emit the X operand of the fp16-pair tensor-core product from the v6 they write
 tfqmrgpuStatus_t launch_vecop_xop(Plan const &p, int op, cudaStream_t stream);
 // v[bpos[b]] += scal * B[b]   (linalg.hxx:383-428)
@@ -174,6 +212,11 @@ tfqmrgpuStatus_t permute_v3(Plan const &p, float *dst_storage, float const *src_
 
 // ---- solver driver (solver.cu) --------------------------------------------------------------------
 tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIterations);
+// the pieces of solve(), for the in-process multi-GPU driver (multi.cu) which interleaves them over the shards
+tfqmrgpuStatus_t solve_begin(Plan &p, cudaStream_t stream, double tolerance, int maxIterations);   // initial state, v5 := b, INIT
+tfqmrgpuStatus_t enqueue_iteration(Plan &p, cudaStream_t stream, cudaEvent_t const *events);      // K1 .. K4
+tfqmrgpuStatus_t enqueue_probe(Plan &p, cudaStream_t stream);                                     // A*v1 - b, N3
+tfqmrgpuStatus_t solve_finish(Plan &p, Control const &fin, int bodies, double launches);           // bookkeeping from the final control block
 
 // register tile of the SpMM kernel (shared by plan.cu's unit builder and spmm.cu)
 constexpr int spmm_tj(bool is_double, int LN) {

@@ -46,6 +46,7 @@ template <typename real_t> struct VecArgs {
     // that write those vectors, tile maxima scratch, and the operand itself with its column scales (written by K1 / K3)
     float *mx4, *mx5, *mx6, *partmax, *xs, *xsinv;
     uint4 *xop;
+    double *slot_out;         // column-sharded runs: where K4 / N3 export (max, count, count) instead of deciding
 };
 
 template <typename T, int N> struct alignas(sizeof(T)*N) Vec { T v[N]; };
@@ -113,6 +114,53 @@ __device__ __forceinline__ void decT(VecArgs<real_t> const &a, uint32_t c, int j
     if (a.status[s] < 0) { a.eta[r] = 0; a.eta[m] = 0; }
     else { a.eta[r] = real_t(-cosi*double(a.alfa[r])); a.eta[m] = real_t(-cosi*double(a.alfa[m])); }
     if (with_c67) { a.c67[r] = r67; a.c67[m] = 0; }
+}
+
+// ---- the reference's host logic after an iteration / after a residual probe, evaluated on the device -------------
+// m0 = max over right-hand sides of tau/|b|^2, m1 / m2 = right-hand sides with status -2 / -1 (core.hxx:239-260)
+__device__ __forceinline__ void decide_iteration(Control &ctl, double m0, double m1, double m2, long long nRHS) {
+    int const it = ctl.iteration + 1;
+    double const max_bound2 = m0*(2*it + 1);                        // core.hxx:252
+    bool const probe = (max_bound2 <= ctl.target_bound2) || (it >= ctl.max_iterations); // core.hxx:254
+    ctl.iteration = it;
+    ctl.max_bound2 = max_bound2;
+    if (nRHS == (long long)(m1 + m2)) {                             // core.hxx:255-260
+        ctl.result = TFQMRGPU_STATUS_BREAKDOWN;
+        ctl.state = STATE_DONE;
+    } else {
+        ctl.state = probe ? STATE_PROBE : STATE_RUN;
+    }
+}
+// m0 = max over right-hand sides of the true relative residual^2, m1 = right-hand sides that are not done (core.hxx:274-298)
+__device__ __forceinline__ void decide_probe(Control &ctl, double m0, double m1) {
+    double max_res2 = 1.4e-76;                                      // core.hxx:274
+    max_res2 = (max_res2 < m0) ? m0 : max_res2;
+    ctl.residual2_reached = max_res2;                               // core.hxx:287
+    ctl.target_bound2 = (ctl.max_bound2/max_res2)*ctl.tol2;        // core.hxx:290
+    ctl.probes += 1;
+    if (0 == m1) {                                                  // isDone, core.hxx:294-298
+        ctl.iterations_needed = ctl.iteration;
+        ctl.result = TFQMRGPU_STATUS_SUCCESS;
+        ctl.state = STATE_DONE;
+    } else {
+        ctl.state = (ctl.iteration < ctl.max_iterations) ? STATE_RUN : STATE_DONE;
+    }
+}
+
+// Column-sharded runs (several GPUs, each with a range of the right-hand-side block columns): the iteration count and the probe
+// schedule of the reference are GLOBAL (one maximum over all right-hand sides, core.hxx:239-299).  K4 / N3 of a shard then only
+// export their partial (max, count, count) and, once every shard's triple is there, every shard takes the same decision.
+// kind 0: after K4, kind 1: after N3.  slots: [nShards][4] doubles of this kind and iteration parity.
+__global__ void decide_kernel(Control *ctl, double const *slots, int nShards, long long nRHS, int kind) {
+    if (ctl->state != ((0 == kind) ? STATE_RUN : STATE_PROBE)) return;
+    double m0 = 0, m1 = 0, m2 = 0;
+    for (int s = 0; s < nShards; ++s) {
+        double const x0 = *reinterpret_cast<double const volatile*>(&slots[4*s + 0]);
+        m0 = (m0 < x0) ? x0 : m0;
+        m1 += *reinterpret_cast<double const volatile*>(&slots[4*s + 1]);
+        m2 += *reinterpret_cast<double const volatile*>(&slots[4*s + 2]);
+    }
+    if (0 == kind) decide_iteration(*ctl, m0, m1, m2, nRHS); else decide_probe(*ctl, m0, m1);
 }
 
 template <int OP> struct OpTraits;
@@ -480,33 +528,12 @@ vec_kernel(VecArgs<real_t> const a)
     if (0 == tid) {
         Control &ctl = *a.ctl;
         ctl.cols_done = 0;
-        if (OP == OP_K4) {
-            int const it = ctl.iteration + 1;
-            double const max_bound2 = m0*(2*it + 1);                        // core.hxx:252
-            bool probe = (max_bound2 <= ctl.target_bound2) || (it >= ctl.max_iterations); // core.hxx:254
-            int const nRHS = int(a.nCols)*LN;
-            ctl.iteration = it;
-            ctl.max_bound2 = max_bound2;
-            if (nRHS == int(m1 + m2)) {                                     // core.hxx:255-260
-                ctl.result = TFQMRGPU_STATUS_BREAKDOWN;
-                ctl.state = STATE_DONE;
-            } else {
-                ctl.state = probe ? STATE_PROBE : STATE_RUN;
-            }
-        }
-        if (OP == OP_N3) {
-            double max_res2 = 1.4e-76;                                      // core.hxx:274
-            max_res2 = (max_res2 < m0) ? m0 : max_res2;
-            ctl.residual2_reached = max_res2;                               // core.hxx:287
-            ctl.target_bound2 = (ctl.max_bound2/max_res2)*ctl.tol2;        // core.hxx:290
-            ctl.probes += 1;
-            if (0 == m1) {                                                  // isDone, core.hxx:294-298
-                ctl.iterations_needed = ctl.iteration;
-                ctl.result = TFQMRGPU_STATUS_SUCCESS;
-                ctl.state = STATE_DONE;
-            } else {
-                ctl.state = (ctl.iteration < ctl.max_iterations) ? STATE_RUN : STATE_DONE;
-            }
+        if (a.slot_out) {            // column-sharded run: export this shard's part, decide_kernel follows
+            a.slot_out[0] = m0; a.slot_out[1] = m1; a.slot_out[2] = m2; a.slot_out[3] = 0;
+            __threadfence_system();
+        } else {
+            if (OP == OP_K4) decide_iteration(ctl, m0, m1, m2, (long long)(a.nCols)*LN);
+            if (OP == OP_N3) decide_probe(ctl, m0, m1);
         }
     }
 }
@@ -518,7 +545,7 @@ vec_kernel(VecArgs<real_t> const a)
 //   K1: max|v6'| <= max|v5| + (|Re beta| + |Im beta|) max|v6|      K3: max|v6'| <= max|v6| + (|Re alfa| + |Im alfa|) max|v4|
 // (maxima over Re and Im parts, kept per column by the kernels that wrote those vectors), so no second pass is needed; fp16
 // being a floating-point format, a bound that is loose by a few binades costs range (29 binades are there), not precision.
-// Thread = (k-octet, lane j): its 8 k values of Re and Im are the 16-byte chunks of the operand rows (Re, j) and (Im, j);
+// Thread = (k-octet, lane j): its 8 k values of Re and Im are four 16-byte chunks (two hi, two lo) of operand row j;
 // all global accesses are coalesced over j.  The arithmetic statements are those of vec_kernel (reference: core.hxx:194,216-220).
 __device__ __forceinline__ float xop_scale_for_bound(float bound) {
     float const b = bound*1.0001f;                       // (the bound itself was rounded)
@@ -533,7 +560,7 @@ __device__ __forceinline__ uint32_t xop_pack2(__half a, __half b) {
     return uint32_t(__half_as_ushort(a)) | (uint32_t(__half_as_ushort(b)) << 16);
 }
 
-template <int OP, int LM, int LN>
+template <int OP, int LM, int LN, bool PLANAR>
 __global__ void __launch_bounds__(256)
 vec_xop_kernel(VecArgs<float> const a)
 {
@@ -608,6 +635,7 @@ vec_xop_kernel(VecArgs<float> const a)
                 a.v7[ore + kk*LN] = yr[kk]; a.v7[oim + kk*LN] = yi[kk];
             }
         }
+        if (PLANAR) {
         uint32_t hr[4], lr[4], hi_[4], li_[4];
         #pragma unroll
         for (int kk = 0; kk < 8; kk += 2) {
@@ -635,6 +663,28 @@ vec_xop_kernel(VecArgs<float> const a)
         }
         dre[0] = make_uint4(hr[0], hr[1], hr[2], hr[3]);       dim_[0] = make_uint4(hi_[0], hi_[1], hi_[2], hi_[3]);
         dre[lo_off] = make_uint4(lr[0], lr[1], lr[2], lr[3]);  dim_[lo_off] = make_uint4(li_[0], li_[1], li_[2], li_[3]);
+            } else {
+        // operand row j: (Re, Im) pairs of halves along k; this thread's 8 k values = two hi chunks and two lo chunks
+        uint32_t hw[8], lw[8];
+        #pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            a.v6[ore + kk*LN] = zr[kk]; a.v6[oim + kk*LN] = zi[kk];
+            vmax = fmaxf(vmax, fmaxf(fabsf(zr[kk]), fabsf(zi[kk])));
+            float const vr = zr[kk]*scale, vi = zi[kk]*scale;
+            __half const hr = __float2half_rn(vr), hi = __float2half_rn(vi);
+            __half const lr = __float2half_rn((vr - __half2float(hr))*2048.f), li = __float2half_rn((vi - __half2float(hi))*2048.f);
+            hw[kk] = xop_pack2(hr, hi); lw[kk] = xop_pack2(lr, li);
+        }
+        uint4 *dst; int lo_off, rows;
+        if (64 == LM) {       // 2 x 2 sub-blocks (k/32, j/32) in the 32 x 32 layout: 16 chunks x 32 rows each
+            int const kh = ko >> 2, q = 2*(ko & 3), jh = j >> 5;
+            dst = a.xop + (size_t(blk)*4 + kh*2 + jh)*(16*32) + size_t(q)*32 + (j & 31); lo_off = 8*32; rows = 32;
+        } else {
+            dst = a.xop + size_t(blk)*((LM/2)*LN) + size_t(2*ko)*LN + j; lo_off = (LM/4)*LN; rows = LN;
+        }
+        dst[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);             dst[rows] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+        dst[lo_off] = make_uint4(lw[0], lw[1], lw[2], lw[3]);        dst[lo_off + rows] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+            }
     }
 
     // ---- max|v6| of this column for the next bound: tile maximum, the last tile folds ---------------------------------
@@ -686,6 +736,7 @@ VecArgs<real_t> make_args(Plan const &p) {
     int sh = 0; while ((1 << sh) < p.LM) ++sh;
     a.lmShift = sh;
     a.mx4 = a.mx5 = a.mx6 = a.partmax = a.xs = a.xsinv = nullptr; a.xop = nullptr;
+    a.slot_out = nullptr;
     if (p.use_tc16) {
         size_t const n = size_t(p.nCols)*p.LN;
         a.mx4 = ws<float>(p, p.off_mx); a.mx5 = a.mx4 + n; a.mx6 = a.mx5 + n;
@@ -709,10 +760,12 @@ void launch_one(Plan const &p, cudaStream_t stream) {
         smem *= sizeof(double);
     }
     constexpr bool kWritesV45 = (OP == OP_INIT || OP == OP_E1 || OP == OP_K2 || OP == OP_E2);
+    VecArgs<real_t> args = make_args<real_t>(p);
+    if ((OP == OP_K4 || OP == OP_N3) && p.exch.slots) args.slot_out = exchange_slots(p, (OP == OP_K4) ? 0 : 1) + 4*p.exch.shard;
     if (std::is_same<real_t, float>::value && kWritesV45 && p.use_tc16)
-        vec_kernel<real_t, VEC, OP, std::is_same<real_t, float>::value && kWritesV45><<<p.nTiles, threads, smem, stream>>>(make_args<real_t>(p));
+        vec_kernel<real_t, VEC, OP, std::is_same<real_t, float>::value && kWritesV45><<<p.nTiles, threads, smem, stream>>>(args);
     else
-        vec_kernel<real_t, VEC, OP, false><<<p.nTiles, threads, smem, stream>>>(make_args<real_t>(p));
+        vec_kernel<real_t, VEC, OP, false><<<p.nTiles, threads, smem, stream>>>(args);
 }
 
 template <typename real_t, int VEC>
@@ -732,14 +785,25 @@ void launch_op(Plan const &p, int op, cudaStream_t stream) {
 
 } // namespace
 
+// every shard's decision from all shards' exported parts (kind 0: after K4, kind 1: after N3)
+tfqmrgpuStatus_t launch_decide(Plan const &p, int kind, cudaStream_t stream)
+{
+    if (nullptr == p.exch.slots) return TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED);
+    decide_kernel<<<1, 1, 0, stream>>>(ws<Control>(p, p.off_ctl), exchange_slots(p, kind), p.exch.nshards, p.exch.nrhs_global, kind);
+    TFQ_CUDA(cudaGetLastError());
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
 // K1 / K3 that also emit the tensor-core product's X operand from the v6 they write (plans with use_tc16 only)
 tfqmrgpuStatus_t launch_vecop_xop(Plan const &p, int op, cudaStream_t stream)
 {
     if (!p.use_tc16 || (OP_K1 != op && OP_K3 != op)) return TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED);
     VecArgs<float> const a = make_args<float>(p);
 #define TFQ_VX(LM, LN) case LM*1000 + LN: \
-        if (OP_K1 == op) vec_xop_kernel<OP_K1, LM, LN><<<p.nTiles, 256, 0, stream>>>(a); \
-        else             vec_xop_kernel<OP_K3, LM, LN><<<p.nTiles, 256, 0, stream>>>(a); \
+        if (p.tc_planar) { if (OP_K1 == op) vec_xop_kernel<OP_K1, LM, LN, true><<<p.nTiles, 256, 0, stream>>>(a); \
+                           else             vec_xop_kernel<OP_K3, LM, LN, true><<<p.nTiles, 256, 0, stream>>>(a); } \
+        else             { if (OP_K1 == op) vec_xop_kernel<OP_K1, LM, LN, false><<<p.nTiles, 256, 0, stream>>>(a); \
+                           else             vec_xop_kernel<OP_K3, LM, LN, false><<<p.nTiles, 256, 0, stream>>>(a); } \
         break;
     switch (p.LM*1000 + p.LN) {
         TFQ_VX(16, 16) TFQ_VX(16, 32) TFQ_VX(16, 64) TFQ_VX(32, 32) TFQ_VX(32, 64) TFQ_VX(64, 64)
