@@ -108,13 +108,27 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getDevices(tfqmrgpuBsrsvPlan_t plan, int *nDevi
  *     the other shards' convergence monitors it calls hook(ctx, slots + offset, nShards*4, stream): the hook must all-gather,
  *     in place and on `stream`, the nShards blocks of 4 doubles starting at the pointer it is given (block `shard` is this
  *     rank's contribution; NCCL: ncclAllGather(ptr + 4*shard, ptr, 4, ncclDouble, comm, stream)).  nRhsGlobal = number of
- *     right-hand sides over all shards.  hook == NULL removes the exchange.  tileBlocksHint: blocks per vector tile of the
- *     UNSHARDED problem (getPlanInfo of a global plan, or 0) - with it a shard reproduces the single-GPU bits of its columns. */
+ *     right-hand sides over all shards.  hook == NULL removes the exchange.
+ *     setShardHints (before bufferSize): X blocks per vector tile (tfqmrgpux_tileBlocksFor) and block columns per block row of
+ *     the UNSHARDED problem - with them a shard tiles its vectors and chooses its product kernel like the single-GPU plan and
+ *     reproduces the single-GPU bits of its columns when every block row of X holds the same block columns (a dense X, the
+ *     reference's use case); for ragged X patterns the products group a row's entries by the block columns that share a
+ *     unit, and results agree to rounding (same iteration count unless a decision falls within that rounding). */
 typedef int32_t (*tfqmrgpuxExchange_t)(void *ctx, double *slots, int count, cudaStream_t stream);
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_setShardExchange(tfqmrgpuBsrsvPlan_t plan, int shard, int nShards, int64_t nRhsGlobal,
     double *slots, tfqmrgpuxExchange_t hook, void *ctx);
-tfqmrgpuStatus_t tfqmrgpux_bsrsv_setTileHint(tfqmrgpuBsrsvPlan_t plan, int64_t tileBlocksHint);
+/* Replicated A without N uploads of the whole operator: the block rows of A are cut into nParts ranges (balanced by blocks);
+ * rank `part` uploads and converts ITS range only - valPart points to the first block of that range in the caller's host array -
+ * and the ranks then exchange the converted ranges device to device (NCCL broadcast / all-gather of the byte windows).
+ * info[0..5] = byte offset and length (inside the workspace) of the converted blocks of the range, byte offset and length of its
+ * row scales (0 length for plans without them), first block and number of blocks of the range.  getMatrixPartInfo only reports. */
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getMatrixPartInfo(tfqmrgpuBsrsvPlan_t plan, int part, int nParts, int64_t info[6]);
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setMatrixPart(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, void const *valPart, char precision,
+    char transposition, tfqmrgpuDataLayout_t layout, int part, int nParts, int64_t info[6]);
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setShardHints(tfqmrgpuBsrsvPlan_t plan, int64_t tileBlocksHint, int32_t maxColsPerRowHint);
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_getTileBlocks(tfqmrgpuBsrsvPlan_t plan, int64_t *tileBlocks);
+/* what bufferSize would choose for a plan with nnzbX X blocks of blockBytes on the current device (the hint for the shards) */
+tfqmrgpuStatus_t tfqmrgpux_tileBlocksFor(int64_t nnzbX, int64_t blockBytes, int64_t *tileBlocks);
 
 #ifdef __cplusplus
 }

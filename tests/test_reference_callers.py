@@ -95,6 +95,21 @@ def test_bench_cli_multiply_on_the_reference_plan(tmp_path):
         assert m and float(m.group(1)) > 1000., txt[-1500:]
 
 
+@pytest.mark.parametrize("lmln", [(32, 32), (32, 64), (64, 64)], ids=lambda v: f"{v[0]}x{v[1]}")
+def test_bench_cli_multiply_other_block_sizes_print_no_warning(lmln, tmp_path):
+    """`bench_tfqmrgpu multiply <plan> f 1 1 LM LN`: the harness prints "Warning! GPU result has large deviations" and withholds the
+    performance line when maxdev > 1e-4 (bench_tfqmrgpu.cu:414).  On this library's default tensor-core product it must not."""
+    from tfqmrgpu_b200 import formats as F
+    g = np.load(os.path.join(ROOT, "tests", "golden", "plan_unordered.npz"))
+    plan = str(tmp_path / "plan_unordered.14-287-16")
+    F.write_multiplication_plan(plan, g["starts"], g["pairs"], int(g["nnz"][1]), int(g["nnz"][2]))
+    txt = _cli("multiply", plan, "f", "1", "1", str(lmln[0]), str(lmln[1]))
+    assert "Warning" not in txt, txt[-1500:]
+    m = re.search(r"# GPU maxdev ([0-9.e+-]+) avgdev ([0-9.e+-]+)", txt)
+    assert m and float(m.group(1)) <= 1e-4, txt[-1500:]
+    assert "# GPU performance" in txt
+
+
 @pytest.mark.skipif(not _have("bench_tfqmrgpu_ours"), reason="reference bench not built")
 def test_bench_cli_tfqmr_matches_the_reference_harness(tmp_path):
     """`tfQMR <file> z`: same `# GPU maxdev ... avgdev ...` line as the reference's harness linked against this library, for the

@@ -34,6 +34,8 @@ EXT_SYMBOLS = [
     "tfqmrgpux_bsrsv_setV3", "tfqmrgpux_bsrsv_getV3", "tfqmrgpux_bsrsv_multiply", "tfqmrgpux_bsrsv_getVector",
     "tfqmrgpux_bsrsv_getWindow", "tfqmrgpux_bsrsv_getRhsStatus", "tfqmrgpux_bsrsv_getSolveStats", "tfqmrgpux_randomShadow",
     "tfqmrgpux_bsrsv_setProfiling", "tfqmrgpux_bsrsv_getSolveProfile", "tfqmrgpux_bsrsv_setOperator",
+    "tfqmrgpux_bsrsv_setDevices", "tfqmrgpux_bsrsv_getDevices", "tfqmrgpux_bsrsv_setShardExchange",
+    "tfqmrgpux_bsrsv_setShardHints", "tfqmrgpux_bsrsv_getMatrixPartInfo", "tfqmrgpux_bsrsv_setMatrixPart", "tfqmrgpux_bsrsv_getTileBlocks", "tfqmrgpux_tileBlocksFor",
 ]
 FORTRAN_SYMBOLS = [
     "tfqmrgpuprinterror_", "tfqmrgpucreatehandle_", "tfqmrgpudestroyhandle_", "tfqmrgpusetstream_",
@@ -118,6 +120,16 @@ def load():
     lib.tfqmrgpux_bsrsv_setProfiling.restype = st; lib.tfqmrgpux_bsrsv_setProfiling.argtypes = [vp, C.c_int]
     lib.tfqmrgpux_bsrsv_getSolveProfile.restype = st; lib.tfqmrgpux_bsrsv_getSolveProfile.argtypes = [vp, C.POINTER(C.c_double)]
     lib.tfqmrgpux_bsrsv_setOperator.restype = st; lib.tfqmrgpux_bsrsv_setOperator.argtypes = [vp, vp, vp]
+    lib.tfqmrgpux_bsrsv_setDevices.restype = st; lib.tfqmrgpux_bsrsv_setDevices.argtypes = [vp, vp, C.c_int, i32p]
+    lib.tfqmrgpux_bsrsv_getDevices.restype = st; lib.tfqmrgpux_bsrsv_getDevices.argtypes = [vp, C.POINTER(C.c_int), i32p, C.c_int]
+    lib.tfqmrgpux_bsrsv_setShardExchange.restype = st
+    lib.tfqmrgpux_bsrsv_setShardExchange.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp]
+    lib.tfqmrgpux_bsrsv_setShardHints.restype = st; lib.tfqmrgpux_bsrsv_setShardHints.argtypes = [vp, C.c_int64, C.c_int32]
+    lib.tfqmrgpux_bsrsv_getTileBlocks.restype = st; lib.tfqmrgpux_bsrsv_getTileBlocks.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.tfqmrgpux_bsrsv_getMatrixPartInfo.restype = st; lib.tfqmrgpux_bsrsv_getMatrixPartInfo.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+    lib.tfqmrgpux_bsrsv_setMatrixPart.restype = st
+    lib.tfqmrgpux_bsrsv_setMatrixPart.argtypes = [vp, vp, vp, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+    lib.tfqmrgpux_tileBlocksFor.restype = st; lib.tfqmrgpux_tileBlocksFor.argtypes = [C.c_int64, C.c_int64, C.POINTER(C.c_int64)]
     _lib = lib
     return lib
 

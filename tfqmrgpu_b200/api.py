@@ -234,6 +234,63 @@ class BsrsvPlan:
         _check(self.lib.tfqmrgpux_bsrsv_getSolveProfile(self.plan, s), "getSolveProfile")
         return dict(solve_ms=s[0], spmm_ms=s[1], spmm_launches=int(s[2]), iterations=int(s[3]), launches=int(s[4]), probes=int(s[5]))
 
+    # ---- several GPUs (include/tfqmrgpu_b200_ext.h) -------------------------------------------------
+    def set_devices(self, n_devices: int, devices=None):
+        """One process, several devices: shard the right-hand-side block columns over `n_devices` GPUs (call before
+        buffer_size_for).  From then on the ordinary calls drive all devices."""
+        d = None if devices is None else np.ascontiguousarray(devices, np.int32)
+        _check(self.lib.tfqmrgpux_bsrsv_setDevices(self.handle.h, self.plan, int(n_devices),
+                                                   None if d is None else d.ctypes.data_as(C.POINTER(C.c_int32))), "setDevices")
+
+    def get_devices(self) -> list[int]:
+        n = C.c_int(0)
+        d = np.zeros(64, np.int32)
+        _check(self.lib.tfqmrgpux_bsrsv_getDevices(self.plan, C.byref(n), d.ctypes.data_as(C.POINTER(C.c_int32)), 64), "getDevices")
+        return [int(v) for v in d[:n.value]] if n.value > 1 else []
+
+    def set_shard_exchange(self, shard: int, n_shards: int, n_rhs_global: int, slots_ptr: int, hook):
+        """One process per GPU: register the per-iteration exchange of the convergence monitors that keeps the reference's
+        GLOBAL iteration / probe rule.  ``hook(slots_ptr, count, stream) -> int`` must all-gather, in place and on `stream`,
+        the ``n_shards`` blocks of 4 doubles starting at ``slots_ptr`` (block `shard` is this rank's).  ``hook=None`` removes it."""
+        proto = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
+        if hook is None:
+            self._exch_keepalive = None
+            _check(self.lib.tfqmrgpux_bsrsv_setShardExchange(self.plan, 0, 1, 0, None, None, None), "setShardExchange")
+            return
+
+        def trampoline(_ctx, slots, count, stream):
+            try:
+                return int(hook(int(slots or 0), int(count), int(stream or 0)) or 0)
+            except Exception:          # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return L.UNDOCUMENTED_ERROR
+        cb = proto(trampoline)
+        self._exch_keepalive = cb
+        _check(self.lib.tfqmrgpux_bsrsv_setShardExchange(self.plan, int(shard), int(n_shards), int(n_rhs_global),
+                                                         C.c_void_p(int(slots_ptr)), C.cast(cb, C.c_void_p), None), "setShardExchange")
+
+    def matrix_part_info(self, part: int, n_parts: int) -> dict:
+        """Row range `part` of `n_parts` of A: byte windows of its converted blocks and row scales inside the workspace."""
+        info = (C.c_int64*6)()
+        _check(self.lib.tfqmrgpux_bsrsv_getMatrixPartInfo(self.plan, int(part), int(n_parts), info), "getMatrixPartInfo")
+        return dict(off=int(info[0]), length=int(info[1]), scale_off=int(info[2]), scale_length=int(info[3]), block0=int(info[4]), nblocks=int(info[5]))
+
+    def set_matrix_part(self, raw_ptr: int, part: int, n_parts: int, trans="n", layout=L.LAYOUT_RIRIRIRI) -> dict:
+        """Upload and convert row range `part` of A; `raw_ptr` points to the FIRST BLOCK OF THAT RANGE in host memory."""
+        info = (C.c_int64*6)()
+        _check(self.lib.tfqmrgpux_bsrsv_setMatrixPart(self.handle.h, self.plan, C.c_void_p(int(raw_ptr)), self.precision.encode(),
+                                                     trans.encode(), layout, int(part), int(n_parts), info), "setMatrixPart")
+        return dict(off=int(info[0]), length=int(info[1]), scale_off=int(info[2]), scale_length=int(info[3]), block0=int(info[4]), nblocks=int(info[5]))
+
+    def set_shard_hints(self, tile_blocks: int, max_cols_per_row: int = 0):
+        _check(self.lib.tfqmrgpux_bsrsv_setShardHints(self.plan, int(tile_blocks), int(max_cols_per_row)), "setShardHints")
+
+    def tile_blocks(self) -> int:
+        v = C.c_int64(0)
+        _check(self.lib.tfqmrgpux_bsrsv_getTileBlocks(self.plan, C.byref(v)), "getTileBlocks")
+        return int(v.value)
+
     def close(self):
         if self.plan:
             self.lib.tfqmrgpu_bsrsv_destroyPlan(self.handle.h, self.plan)
@@ -248,6 +305,13 @@ class BsrsvPlan:
             self.close()
         except Exception:
             pass
+
+
+def tile_blocks_for(nnzbX: int, block_bytes: int) -> int:
+    """X blocks per vector tile that bufferSize chooses for a plan with nnzbX blocks of block_bytes on the current device."""
+    v = C.c_int64(0)
+    _check(L.load().tfqmrgpux_tileBlocksFor(int(nnzbX), int(block_bytes), C.byref(v)), "tileBlocksFor")
+    return int(v.value)
 
 
 def bsrsv(precision, mb, lm, ln, rpA, ciA, valA, transA, rpX, ciX, transX, rpB, ciB, valB, transB,

@@ -630,9 +630,65 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_setShardExchange(tfqmrgpuBsrsvPlan_t plan, int 
     p.exch.hook = hook; p.exch.hook_ctx = ctx; p.exch.parity = 0;
     return TFQMRGPU_STATUS_SUCCESS;
 }
-tfqmrgpuStatus_t tfqmrgpux_bsrsv_setTileHint(tfqmrgpuBsrsvPlan_t plan, int64_t tileBlocksHint) {
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setShardHints(tfqmrgpuBsrsvPlan_t plan, int64_t tileBlocksHint, int32_t maxColsPerRowHint) {
     if (nullptr == plan) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
-    P(plan)->tile_blocks_hint = (tileBlocksHint > 0) ? size_t(tileBlocksHint) : 0;     // takes effect with the next bufferSize
+    P(plan)->tile_blocks_hint = (tileBlocksHint > 0) ? size_t(tileBlocksHint) : 0;     // take effect with the next bufferSize
+    P(plan)->max_cols_hint = (maxColsPerRowHint > 0) ? maxColsPerRowHint : 0;
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+static tfqmrgpuStatus_t matrix_part(Plan const &p, int part, int nParts, int64_t info[6], int &row0, int &row1) {
+    if (nParts < 1 || part < 0 || part >= nParts || nullptr == info) return TFQ_ERR(TFQMRGPU_UNDOCUMENTED_ERROR);
+    if (!p.configured || p.multi || p.h_rpA.size() != size_t(p.mb) + 1) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    auto row_at = [&](int q) {      // first block row at or after q/nParts of the blocks
+        int32_t const target = int32_t((int64_t(p.nnzbA)*q + nParts/2)/nParts);
+        return int(std::lower_bound(p.h_rpA.begin(), p.h_rpA.end(), target) - p.h_rpA.begin());
+    };
+    row0 = (0 == part) ? 0 : std::min(p.mb, row_at(part));
+    row1 = (nParts - 1 == part) ? p.mb : std::min(p.mb, row_at(part + 1));
+    if (row1 < row0) row1 = row0;
+    size_t const blockBytes = 2*size_t(p.LM)*p.LM*(('z' == p.precision) ? 8 : 4);
+    int64_t const b0 = p.h_rpA[row0], b1 = p.h_rpA[row1];
+    info[0] = int64_t(p.off_A + size_t(b0)*blockBytes); info[1] = (b1 - b0)*int64_t(blockBytes);
+    info[2] = int64_t(p.off_ainv + size_t(row0)*4);     info[3] = p.use_tc16 ? int64_t(row1 - row0)*4 : 0;
+    info[4] = b0; info[5] = b1 - b0;
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getMatrixPartInfo(tfqmrgpuBsrsvPlan_t plan, int part, int nParts, int64_t info[6]) {
+    if (nullptr == plan) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    int r0, r1;
+    return matrix_part(*P(plan), part, nParts, info, r0, r1);
+}
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setMatrixPart(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, void const *valPart, char precision,
+    char transposition, tfqmrgpuDataLayout_t layout, int part, int nParts, int64_t info[6]) {
+    if (nullptr == plan || nullptr == handle) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan &p = *P(plan);
+    bool trans = false; double scal_imag = 1;
+    tfqmrgpuStatus_t st = parse_layout_trans(layout, transposition, trans, scal_imag);
+    if (st) return st;
+    trans = !trans;                      // A is stored transposed [k][i] (tfqmrgpu.cu:509-520)
+    int row0, row1;
+    st = matrix_part(p, part, nParts, info, row0, row1);
+    if (st) return st;
+    if (nullptr == p.pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    bool const is_double = ('z' == p.precision);
+    if (('z' == lower(precision)) != is_double) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, precision);
+    if (info[5] < 1) return TFQMRGPU_STATUS_SUCCESS;
+    if (nullptr == valPart) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    cudaStream_t const stream = static_cast<Handle*>(handle)->stream;
+    char *const dst = p.pBuffer + info[0];
+    uint32_t const b0 = uint32_t(info[4]), nb = uint32_t(info[5]);
+    TFQ_CUDA(cudaMemcpyAsync(dst, valPart, size_t(info[1]), cudaMemcpyHostToDevice, stream));
+    st = convert_inplace(p, dst, nb, p.LM, p.LM, is_double, layout, trans, scal_imag, stream, p.use_tc);
+    if (TFQMRGPU_STATUS_SUCCESS == st && p.use_tc16) st = launch_aop_blockmax(p, b0, nb, stream);
+    if (TFQMRGPU_STATUS_SUCCESS == st && p.use_tc16) st = launch_aop_convert_rows(p, row0, row1, stream);
+    return st;
+}
+tfqmrgpuStatus_t tfqmrgpux_tileBlocksFor(int64_t nnzbX, int64_t blockBytes, int64_t *tileBlocks) {
+    if (nullptr == tileBlocks || nnzbX < 0 || blockBytes < 1) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    *tileBlocks = int64_t(plan_tile_blocks(size_t(nnzbX), size_t(blockBytes), nsm));
     return TFQMRGPU_STATUS_SUCCESS;
 }
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_getTileBlocks(tfqmrgpuBsrsvPlan_t plan, int64_t *tileBlocks) {

@@ -215,6 +215,7 @@ tfqmrgpuStatus_t multi_buffer_size(Plan &p, int LM, int LN, char prec, size_t *b
         sp.pBuffer = nullptr; sp.bufferBytes = 0; sp.v3_ready = false; sp.configured = false;
         plan_drop_graph(sp);
         sp.tile_blocks_hint = tile_blocks;
+        sp.max_cols_hint = p.maxColsPerRow;
         tfqmrgpuStatus_t const st = plan_configure(sp, sh.stream, LM, LN, prec);
         if (TFQMRGPU_STATUS_SUCCESS != st) return st;
         sp.configured = true;

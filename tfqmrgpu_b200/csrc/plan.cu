@@ -446,7 +446,8 @@ tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, ch
         {
             char const *env_small = std::getenv("TFQMRGPU_SMALL");
             bool const allowed = env_small ? (0 != std::atoi(env_small)) : true;
-            p.use_small = allowed && (LM <= 8) && (is_double ? (p.maxColsPerRow*LN <= 16) : (9 != LN));
+            int const cols_per_row = (p.max_cols_hint > 0) ? p.max_cols_hint : p.maxColsPerRow;   // a shard decides like the unsharded plan
+            p.use_small = allowed && (LM <= 8) && (is_double ? (cols_per_row*LN <= 16) : (9 != LN));
         }
         int g = std::max(1, ((p.use_small ? 32 : 128)*TI*TJ)/(LM*LN));
         g = std::min(g, 16);

@@ -97,6 +97,7 @@ struct Plan {
     Exchange exch;
     struct MultiPlan *multi = nullptr;       // in-process multi-GPU plan (multi.cu): this Plan is then only the global analysis
     size_t tile_blocks = 0;                  // X blocks per vector tile chosen by plan_configure
+    int    max_cols_hint = 0;               // ... and choose the product kernel by the unsharded plan's block columns per row
     size_t tile_blocks_hint = 0;             // shards tile their vectors like the unsharded plan (same reduction order, same bits)
     tfqmrgpuxOperator_t user_op = nullptr;   // user-defined operator instead of the block-sparse product (ext header)
     void *user_ctx = nullptr;

@@ -7,10 +7,13 @@ C-ABI with NO data-path collective.  NCCL (via ``torch.distributed``) is only us
 for the gathered X.  The shadow vector v3 of a shard is the matching slice of the 1-GPU cuRAND stream,
 so a shard reproduces the 1-GPU numbers of its columns.
 
-Convergence control: every shard runs the reference's probe rule on ITS columns (the reference takes
-the maximum over all columns of the single GPU, core.hxx:239-299), so a shard whose columns converge
-early stops early; every column still satisfies the reference's stopping criterion.  The reported
-iteration count is the maximum over the shards.
+Convergence control: the reference's iteration counter and probe schedule are GLOBAL - one maximum over
+all right-hand sides decides (core.hxx:239-299).  With a process group (``dist``) every rank registers an
+exchange (``tfqmrgpux_bsrsv_setShardExchange``): after K4 and after N3 the ranks all-gather three numbers
+per shard on the solver's stream (NCCL) and take the same decision, so an N-rank run has the single-GPU
+iteration count and - the shards tile their vectors like the unsharded plan - the single-GPU bits.
+Without a process group (ranks solved one after the other, e.g. on one GPU) every shard runs the rule on
+its own columns and may stop earlier than the global maximum would.
 
 The pure index logic (``partition_columns``, ``shard_pattern``, ``global_block_index``) is numpy-only and
 is what the world_size-2 gloo tests exercise on CPU.
@@ -88,7 +91,7 @@ class ShardedBsrsv:
     optional NCCL gather)."""
 
     def __init__(self, mb, lm, ln, precision, rpA, ciA, valA, transA, rpX, ciX, rpB, ciB, valB, transB,
-                 rank=0, world=1, index_offset=0, device=None, global_v3=True):
+                 rank=0, world=1, index_offset=0, device=None, global_v3=True, dist=None):
         import torch
         from . import api
         self.torch = torch
@@ -105,6 +108,12 @@ class ShardedBsrsv:
         rpA0 = np.asarray(rpA, np.int32) - index_offset
         ciA0 = np.asarray(ciA, np.int32) - index_offset
         self.plan = api.BsrsvPlan(self.handle, mb, rpA0, ciA0, s.rpX, s.ciX, s.rpB, s.ciB, 0, 0)
+        if world > 1:
+            # tile the shard's vectors like the unsharded plan would (same reduction order -> same bits)
+            max_cols = int(np.diff(np.asarray(rpX, np.int64)).max())
+            self.plan.set_shard_hints(api.tile_blocks_for(s.nnzbX_global, 2*lm*ln*(8 if precision == "z" else 4)), max_cols)
+        if dist is not None and world > 1:
+            self._register_exchange(dist, rank, world, s.ncols_global*ln)
         nbytes = self.plan.buffer_size_for(lm, ln, precision)
         self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
         base = self.workspace.data_ptr()
@@ -125,6 +134,23 @@ class ShardedBsrsv:
         valB = np.asarray(valB)
         self.plan.set_matrix("A", valA, transA)
         self.plan.set_matrix("B", valB[s.selB], transB)
+
+    def _register_exchange(self, dist, rank, world, n_rhs_global):
+        """All-gather of the shards' convergence monitors on the solver's stream (the library calls this twice per iteration)."""
+        torch = self.torch
+        self._slots = torch.zeros(2*2*world*4, dtype=torch.float64, device=self.device)
+        self._mine = torch.zeros(4, dtype=torch.float64, device=self.device)
+        base = self._slots.data_ptr()
+
+        def hook(ptr, count, stream):
+            off = (ptr - base)//8
+            view = self._slots[off:off + count]
+            ext = torch.cuda.ExternalStream(stream, device=self.device) if stream else torch.cuda.default_stream(self.device)
+            with torch.cuda.stream(ext):
+                self._mine.copy_(view[4*rank:4*rank + 4])
+                dist.all_gather_into_tensor(view, self._mine)
+            return 0
+        self.plan.set_shard_exchange(rank, world, n_rhs_global, base, hook)
 
     def solve(self, threshold, max_iterations):
         if self.plan is None:
