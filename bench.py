@@ -18,8 +18,10 @@ A "step" is one complete tfQMR solve of that system through the C-ABI of libtfQM
           compiled for sm_100) on the full workload on this GPU and reports them as `reference_gpu` - a reported baseline
           like cpu_baseline, after the timed region, never part of the product path (`--no-cpu` skips both).
 
-N > 1 (torchrun): every rank solves its own 64 right-hand-side columns of a 64*N-column problem with A
-replicated (RHS block-column sharding, no data-path collective); value = all ranks' flops / max time.
+N > 1 (torchrun): every rank solves its own 64 right-hand-side columns of ONE 64*N-column problem with A replicated
+(RHS block-column sharding); the ranks keep the reference's global iteration / probe rule by all-gathering three numbers
+per rank twice per iteration (NCCL); value = all ranks' flops / max time (weak scaling).  `strong`: one problem of
+--strong-rhs columns split over the ranks.  A reaches the GPUs in N ranges over N PCIe links + NCCL broadcasts.
 `--impl reference` times the reference's CPU path on the bounded sample instead (rank 0 only).
 """
 from __future__ import annotations
@@ -173,6 +175,26 @@ def run_reference(args):
     return 0
 
 
+def _make_plan(torch, api, sp, lm, ln, prec, dev, stream=None, shard=None):
+    """Plan + caller-owned workspace (a torch tensor, so that windows of it can be NCCL buffers).  shard = (dist, rank, world,
+    ncols_global): register the exchange that keeps the reference's GLOBAL iteration / probe rule across the ranks."""
+    from tfqmrgpu_b200 import sharded
+    h = api.Handle(stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream)
+    pl = api.BsrsvPlan(h, sp.mb, sp.rpA, sp.ciA, sp.rpX, sp.ciX, sp.rpB, sp.ciB)
+    keep = None
+    if shard is not None:
+        dist, rank, world, ncols_global = shard
+        es = 8 if prec == "z" else 4
+        pl.set_shard_hints(api.tile_blocks_for(sp.mb*ncols_global, 2*lm*ln*es), ncols_global)
+        keep = sharded.NcclExchange(pl, dist, rank, world, ncols_global*ln, dev)
+    nbytes = pl.buffer_size_for(lm, ln, prec)
+    ws_t = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+    ws_ptr = (ws_t.data_ptr() + 255) & ~255
+    pl.set_buffer(ws_ptr, keep_alive=(ws_t, keep))
+    base = ws_ptr - ws_t.data_ptr()
+    return h, pl, ws_t, base, nbytes
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -187,35 +209,6 @@ def run_ours(args):
     n, lm, ln, ncols, prec, tol, maxit = args.n, args.lm, args.ln, args.ncols, args.precision, args.tol, 100
     dt = np.float64 if prec == "z" else np.float32
     es = 8 if prec == "z" else 4
-
-    # this rank's shard: block columns [rank*ncols, (rank+1)*ncols) of a world*ncols-column problem, A replicated
-    sp = synthetic.Stencil27(n, lm, ln, ncols, sigma=args.sigma, dtype=dt, device=dev, col0=rank*ncols, ncols_global=world*ncols,
-                             with_values=(0 == rank))
-    h = api.Handle(torch.cuda.current_stream(dev).cuda_stream)
-    pl = api.BsrsvPlan(h, sp.mb, sp.rpA, sp.ciA, sp.rpX, sp.ciX, sp.rpB, sp.ciB)
-    nbytes = pl.buffer_size_for(lm, ln, prec)
-    # caller-owned workspace as a torch tensor, so that the A window can be the target of an NCCL broadcast
-    ws_t = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
-    ws_ptr = (ws_t.data_ptr() + 255) & ~255
-    pl.set_buffer(ws_ptr, keep_alive=ws_t)
-    a_off, a_len = pl.window("A")
-    a_win = ws_t[(ws_ptr - ws_t.data_ptr()) + a_off:(ws_ptr - ws_t.data_ptr()) + a_off + a_len]
-    info = pl.plan_info()
-    a_ptr = sp.valA_host.data_ptr() if 0 == rank else 0
-    valB = torch.from_numpy(sp.valB).pin_memory()
-    x_host = torch.empty(sp.nnzbX*lm*ln*2, dtype=torch.float64 if prec == "z" else torch.float32).pin_memory()
-    x_np = x_host.numpy()
-
-    def upload(pl=pl, a_win=a_win, stream=None):
-        # A is replicated: rank 0 uploads it over PCIe (setMatrix: H2D + layout conversion) and the converted operand goes
-        # to the other ranks' A windows over NVLink (the only collective of the path; it replaces N-1 PCIe uploads of 7 GB
-        # that would contend for the host's memory bandwidth).  B and X are per rank.  All of it is asynchronous to the host.
-        if world == 1 or rank == 0:
-            pl.set_matrix("A", None, "n", raw_ptr=a_ptr)
-        if world > 1:
-            with torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream(dev)):
-                dist.broadcast(a_win, src=0)
-        pl.set_matrix("B", None, "n", raw_ptr=valB.data_ptr())
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -233,75 +226,109 @@ def run_ours(args):
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.SUM); return float(t.item())
 
+    # this rank's shard: block columns [rank*ncols, (rank+1)*ncols) of ONE world*ncols-column problem, A replicated; the ranks
+    # keep the reference's global iteration / probe rule through the exchange (3 numbers per rank, twice per iteration)
+    ncols_global = world*ncols
+    sp = synthetic.Stencil27(n, lm, ln, ncols, sigma=args.sigma, dtype=dt, device=dev, col0=rank*ncols, ncols_global=ncols_global,
+                             with_values=False)
+    shard = (dist, rank, world, ncols_global) if world > 1 else None
+    h, pl, ws_t, base, nbytes = _make_plan(torch, api, sp, lm, ln, prec, dev, shard=shard)
+    info = pl.plan_info()
+    # every rank uploads ITS row range of A over its own PCIe link (setMatrixPart) and the ranks exchange the converted ranges
+    # device to device; the host values of that range only are generated (and pinned) here
+    parts = [pl.matrix_part_info(r, world) for r in range(world)]
+    mine = parts[rank]
+    valA_part = sp.values_of(mine["block0"], mine["block0"] + mine["nblocks"])
+    valB = torch.from_numpy(sp.valB).pin_memory()
+    x_host = torch.empty(sp.nnzbX*lm*ln*2, dtype=torch.float64 if prec == "z" else torch.float32).pin_memory()
+    x_np = x_host.numpy()
+
+    def upload(pl=pl, ws_t=ws_t, base=base, stream=None):
+        pl.set_matrix_part(valA_part.data_ptr(), rank, world)
+        if world > 1:
+            with torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream(dev)):
+                for r, q in enumerate(parts):      # N broadcasts of 1/N each = an all-gather of ranges of (slightly) different sizes
+                    if q["length"]:
+                        dist.broadcast(ws_t[base + q["off"]:base + q["off"] + q["length"]], src=r)
+                    if q["scale_length"]:
+                        dist.broadcast(ws_t[base + q["scale_off"]:base + q["scale_off"] + q["scale_length"]], src=r)
+        pl.set_matrix("B", None, "n", raw_ptr=valB.data_ptr())
+
     upload()
     statuses = []
     for _ in range(max(args.warmup, 3)):
         statuses.append(pl.solve(tol, maxit))
-    # ---- device-resident metric: K solves, inputs already in HBM ------------------------------------------
-    pl.set_profiling(True)
+    # ---- device-resident metric: K solves, inputs already in HBM; the production path (iteration bodies as CUDA graphs on one
+    #      GPU, exchange hook on several), no profiling events ----------------------------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start(); time.sleep(0.3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    flops = launches = spmm_ms = spmm_n = iters = 0
+    flops = launches = iters = 0
     barrier()
     e0.record()
     for _ in range(args.steps):
         statuses.append(pl.solve(tol, maxit))
-        prof = pl.solve_profile()
-        flops += pl.info()["flops"]; launches += prof["launches"]; spmm_ms += prof["spmm_ms"]; spmm_n += prof["spmm_launches"]
-        iters += prof["iterations"]
+        st_ = pl.solve_stats()
+        flops += pl.info()["flops"]; launches += st_["launches"]; iters += pl.info()["iterations"]
     e1.record()
     barrier()
-    clocks = sampler.stop() if sampler else None
     ms = reduce_max(e0.elapsed_time(e1))
     total_flops = reduce_sum(flops)
     worst_status = int(reduce_max(float(max(statuses[-args.steps:]))))
     iters_max = reduce_max(iters/args.steps); iters_min = -reduce_max(-iters/args.steps)
-    pl.set_profiling(False)
     last = pl.info()
+    # ---- the same K solves once more with CUDA events around every block-sparse product (the roofline's launch durations) -----
+    pl.set_profiling(True)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    spmm_ms = spmm_n = 0
+    barrier()
+    p0.record()
+    for _ in range(args.steps):
+        pl.solve(tol, maxit)
+        prof = pl.solve_profile()
+        spmm_ms += prof["spmm_ms"]; spmm_n += prof["spmm_launches"]
+    p1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_profiled = reduce_max(p0.elapsed_time(p1))
+    pl.set_profiling(False)
 
     # ---- end to end through the C-ABI with host buffers -------------------------------------------------------
-    h2d = sp.a_bytes + valB.numel()*valB.element_size()          # rank 0 (the other ranks upload B only when N > 1)
-    d2h = x_host.numel()*x_host.element_size()
+    h2d = reduce_sum(float(valA_part.numel()*valA_part.element_size() + valB.numel()*valB.element_size()))   # all ranks together
+    d2h = reduce_sum(float(x_host.numel()*x_host.element_size()))
     # Double-buffered, as a caller with a stream of systems would run it: a second plan with its own workspace and stream
-    # takes the upload of step k+1 (asynchronous C-ABI calls: pinned H2D on the plan's copy stream, conversion on its stream)
-    # while step k is being solved.  Every step's A, B go host -> device and its X device -> host inside the timed region.
+    # takes the upload of step k+1 (asynchronous C-ABI calls: pinned H2D, conversion on its stream) while step k is being
+    # solved.  Every step's A, B go host -> device and its X device -> host inside the timed region.
     # If the second workspace cannot be allocated on any rank (a smaller GPU), every rank falls back to one plan: same
     # per-step copies, nothing overlapped.
-    lanes = [(pl, a_win, None, x_np)]
+    lanes = [(pl, ws_t, base, None, x_np)]
     pl2 = h2 = None
     try:
         if os.environ.get("TFQMRGPU_BENCH_NO_PIPELINE"):
             raise RuntimeError("disabled by TFQMRGPU_BENCH_NO_PIPELINE")
         st2 = torch.cuda.Stream(dev)
-        h2 = api.Handle(st2.cuda_stream)
-        pl2 = api.BsrsvPlan(h2, sp.mb, sp.rpA, sp.ciA, sp.rpX, sp.ciX, sp.rpB, sp.ciB)
-        assert pl2.buffer_size_for(lm, ln, prec) == nbytes
-        ws2_t = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
-        ws2_ptr = (ws2_t.data_ptr() + 255) & ~255
-        pl2.set_buffer(ws2_ptr, keep_alive=ws2_t)
-        a2_off, a2_len = pl2.window("A")
-        a2_win = ws2_t[(ws2_ptr - ws2_t.data_ptr()) + a2_off:(ws2_ptr - ws2_t.data_ptr()) + a2_off + a2_len]
+        h2, pl2, ws2_t, base2, nbytes2 = _make_plan(torch, api, sp, lm, ln, prec, dev, stream=st2.cuda_stream, shard=shard)
+        assert nbytes2 == nbytes
         x2_host = torch.empty_like(x_host).pin_memory()
-        lanes.append((pl2, a2_win, st2, x2_host.numpy()))
+        lanes.append((pl2, ws2_t, base2, st2, x2_host.numpy()))
     except Exception as exc:                                  # noqa: BLE001 - any allocation failure means "no second lane"
         print(f"bench: second plan for the double-buffered e2e leg not available ({exc!r}); e2e runs unpipelined", file=sys.stderr)
-    if reduce_max(float(len(lanes) < 2)) > 0:                 # all ranks together (the upload holds a collective)
+    if reduce_max(float(len(lanes) < 2)) > 0:                 # all ranks together (the upload holds collectives)
         lanes = lanes[:1]
     pipelined = len(lanes) > 1
     if pipelined:
-        upload(*lanes[1][:3]); pl2.solve(tol, maxit)        # untimed warm-up of the second plan (graph capture, first touch)
+        upload(*lanes[1][:4]); pl2.solve(tol, maxit)        # untimed warm-up of the second plan (graph capture, first touch)
     e2e_flops = 0
     barrier()
     t0 = time.perf_counter()
-    upload(*lanes[0][:3])
+    upload(*lanes[0][:4])
     for k in range(args.steps):
         if pipelined and k + 1 < args.steps:
-            upload(*lanes[(k + 1) % 2][:3])
+            upload(*lanes[(k + 1) % 2][:4])
         elif not pipelined and k > 0:
-            upload(*lanes[0][:3])
-        cur, _, _, xout = lanes[k % len(lanes)]
+            upload(*lanes[0][:4])
+        cur, _, _, _, xout = lanes[k % len(lanes)]
         cur.solve(tol, maxit)
         cur.get_matrix("X", "n", L.LAYOUT_RIRIRIRI, out=xout)
         e2e_flops += cur.info()["flops"]
@@ -318,11 +345,11 @@ def run_ours(args):
         pl2.close()
     if h2 is not None:
         h2.close()
+    lanes = None
 
     # ---- roofline of the block-sparse product ------------------------------------------------------------------
     nPairs, nnzbX = info["nPairs"], info["nnzbX"]
-    lists_a_used = sp.nnzbA
-    spmm_bytes = lists_a_used*2*lm*lm*es + 2*nnzbX*2*lm*ln*es + 8*nPairs + 4*(nnzbX + 1)   # SURVEY.md 8d formula
+    spmm_bytes = sp.nnzbA*2*lm*lm*es + 2*nnzbX*2*lm*ln*es + 8*nPairs + 4*(nnzbX + 1)   # SURVEY.md 8d formula
     spmm_flops = nPairs*8*lm*lm*ln
     peaks = {}
     try:
@@ -342,34 +369,82 @@ def run_ours(args):
                 "peak_source": "measured" if peaks else "fallback",
                 "launches_timed": int(spmm_n), "avg_launch_ms": spmm_avg_ms, "algorithmic_bytes_per_launch": spmm_bytes,
                 "gflops_per_launch": spmm_flops*1e-9, "achieved_tflops": spmm_flops/(spmm_avg_ms*1e-3)*1e-12 if spmm_n else 0.0,
-                "share_of_step": spmm_ms/max(e0.elapsed_time(e1), 1e-9)}
+                "share_of_step": spmm_ms/max(p0.elapsed_time(p1), 1e-9),
+                "timed_region": f"{args.steps} solves with CUDA events around every product (kernel-by-kernel launches), "
+                                f"{ms_profiled/args.steps:.2f} ms per solve; the headline region runs without them"}
 
     if prec == "z" and spmm_n:
         # complex fp64 (BASELINE configs 4/5): 64 flop/B and more, the product is bound by the FP64 (DMMA) pipe, not by HBM
         tf = spmm_flops/(spmm_avg_ms*1e-3)*1e-12
-        roofline.update({"bound": "tensor", "achieved": tf, "peak": 37.0, "unit": "TFLOP/s", "frac": tf/37.0,
-                         "peak_source": "nominal B200 fp64 (MEASURED_PEAKS.json holds no fp64 figure)",
-                         "hbm_gbs_algorithmic": achieved})
+        fp64 = measured_fp64_peak()
+        roofline.update({"bound": "tensor", "achieved": tf, "peak": fp64["tflops"], "unit": "TFLOP/s", "frac": tf/fp64["tflops"],
+                         "peak_source": fp64["source"], "hbm_gbs_algorithmic": achieved})
+
+    # ---- strong scaling: ONE problem of --strong-rhs right-hand-side columns split over the ranks -------------------------------
+    strong = None
+    if args.strong_rhs > 0 and args.strong_rhs % (ln*world) == 0:
+        pl.close(); h.close(); pl = h = None
+        ws_t = None; valA_keep = valA_part
+        torch.cuda.empty_cache()
+        sc_global = args.strong_rhs//ln
+        sc = sc_global//world
+        sp2 = synthetic.Stencil27(n, lm, ln, sc, sigma=args.sigma, dtype=dt, device=dev, col0=rank*sc, ncols_global=sc_global, with_values=False)
+        hs, ps, wss, bases, nbs = _make_plan(torch, api, sp2, lm, ln, prec, dev, shard=(dist, rank, world, sc_global) if world > 1 else None)
+        parts2 = [ps.matrix_part_info(r, world) for r in range(world)]
+        assert parts2[rank]["block0"] == mine["block0"] and parts2[rank]["nblocks"] == mine["nblocks"]
+        ps.set_matrix_part(valA_keep.data_ptr(), rank, world)
+        if world > 1:
+            for r, q in enumerate(parts2):
+                if q["length"]:
+                    dist.broadcast(wss[bases + q["off"]:bases + q["off"] + q["length"]], src=r)
+                if q["scale_length"]:
+                    dist.broadcast(wss[bases + q["scale_off"]:bases + q["scale_off"] + q["scale_length"]], src=r)
+        ps.set_matrix("B", sp2.valB)
+        for _ in range(2):
+            ps.solve(tol, maxit)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sflops = 0
+        barrier()
+        s0.record()
+        for _ in range(args.steps):
+            sst = ps.solve(tol, maxit); sflops += ps.info()["flops"]
+        s1.record()
+        barrier()
+        sms = reduce_max(s0.elapsed_time(s1))
+        sinfo = ps.info()
+        strong = {"rhs_columns_total": args.strong_rhs, "rhs_columns_per_gpu": sc*ln, "ms_per_solve": sms/args.steps,
+                  "value": reduce_sum(sflops)/(sms*1e-3)*1e-9, "unit": UNIT, "iterations": sinfo["iterations"], "status": int(reduce_max(float(sst))),
+                  "residual_reached": sinfo["residuum"], "workspace_bytes_per_gpu": nbs,
+                  "what": "one problem, right-hand-side block columns split over the GPUs, A replicated, global iteration rule"}
+        ps.close(); hs.close()
+
     line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": total_flops/(ms*1e-3)*1e-9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms/args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64" if prec == "z" else "f32", "data": "synthetic",
-            "config": {"workload": workload_name(n, lm, ln, ncols, prec, tol, args.sigma), "parallelism": f"rhs-column sharding x{world}, A replicated",
+            "config": {"workload": workload_name(n, lm, ln, ncols, prec, tol, args.sigma),
+                       "parallelism": f"one {ncols_global*ln}-column problem, rhs block columns sharded x{world}, A replicated, "
+                                      f"global iteration rule ({'NCCL all-gather of 3 numbers per rank, twice per iteration' if world > 1 else 'single GPU'})",
                        "l2": "working set 12 GB per GPU >> 126 MB L2, no flush needed",
                        "iterations_per_solve": iters/args.steps, "iterations_per_solve_min_max_over_ranks": [iters_min, iters_max],
                        "residual_reached": last["residuum"], "status": int(statuses[-1]), "worst_status_over_ranks": worst_status,
-                       "workspace_bytes": nbytes, "nnzbA": sp.nnzbA, "nnzbX": nnzbX, "nPairs": nPairs},
-            "e2e": {"value": e2e_total/e2e_s*1e-9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "a_distribution": "rank 0 H2D + NCCL broadcast over NVLink" if world > 1 else "H2D",
+                       "workspace_bytes": nbytes, "nnzbA": sp.nnzbA, "nnzbX": nnzbX, "nPairs": nPairs,
+                       "product_kernel": "tcgen05 fp16-pair" if info["use_tc"] else ("dmma" if info["use_dmma"] else "simt")},
+            "e2e": {"value": e2e_total/e2e_s*1e-9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "a_distribution": (f"every rank uploads 1/{world} of A over its own PCIe link, converted ranges exchanged with NCCL broadcasts over NVLink"
+                                       if world > 1 else "H2D"),
                     "ms_per_step": 1e3*e2e_s/args.steps, "pipelining": "2 plans: upload of step k+1 overlaps solve of step k" if pipelined else "none (second workspace not available)",
                     "ms_single_step_unpipelined": 1e3*e2e_serial_s},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "clocks": clocks,
         }
-    pl.close(); h.close()
+        if strong is not None:
+            line["strong"] = strong
+    if pl is not None:
+        pl.close(); h.close()
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             r = cpu_reference_sample(lm, ln, ncols, prec, tol, maxit, repeats=1)
@@ -379,7 +454,8 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": repr(e)[:200]}
         if not args.no_ref_gpu:
             try:
-                line["reference_gpu"] = reference_gpu_same_box(sp, lm, ln, prec, tol, maxit)
+                spf = synthetic.Stencil27(n, lm, ln, ncols, sigma=args.sigma, dtype=dt, device=dev)
+                line["reference_gpu"] = reference_gpu_same_box(spf, lm, ln, prec, tol, maxit)
             except Exception as e:  # informational leg only
                 line["reference_gpu"] = {"error": repr(e)[:200]}
     if rank == 0:
@@ -387,6 +463,19 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def measured_fp64_peak():
+    """FP64 rate of this GPU from tools/fp64_rate (DFMA and DMMA.8x8x4 issue-rate microbenchmark, built by the library's Makefile);
+    the datasheet value when the tool is missing."""
+    exe = os.path.join(ROOT, "tools", "fp64_rate")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        vals = dict(l.split("=") for l in out.stdout.split() if "=" in l)
+        t = max(float(vals["dfma_tflops"]), float(vals["dmma_tflops"]))
+        return {"tflops": t, "source": f"measured (tools/fp64_rate: DFMA {float(vals['dfma_tflops']):.1f}, DMMA {float(vals['dmma_tflops']):.1f} TFLOP/s)"}
+    except Exception:
+        return {"tflops": 37.0, "source": "nominal B200 fp64 (tools/fp64_rate not available)"}
 
 
 def main():
@@ -402,6 +491,9 @@ def main():
     ap.add_argument("--precision", default="c", choices=["c", "z"])
     ap.add_argument("--tol", type=float, default=DEFAULT_TOL)
     ap.add_argument("--sigma", type=float, default=8.0, help="diagonal shift of the stencil operator (8: fp32 config; 1: fp64 configs)")
+    ap.add_argument("--strong-rhs", type=int, default=512, help="right-hand-side columns of the strong-scaling leg (one problem split "
+                    "over the GPUs; 0: skip).  512 columns of the fp32 stencil need 46 GB on one GPU")
+    ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3, 4, 5], help="BASELINE.json configuration (1-based); 3 is the headline")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline (and reference_gpu) legs")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the informational same-box run of the reference's CUDA kernels")
     args = ap.parse_args()

@@ -164,3 +164,36 @@ def test_solve_vs_reference_cuda_build_same_gpu(case):
     assert info["residuum"] <= tol and r["residuum"] <= tol
     scale = np.abs(r["X"]).max()
     assert np.abs(X - r["X"]).max() <= (10 if prec == "z" else 50)*tol*scale
+
+
+@pytest.mark.skipif(not _have("libtfqmr_ref_gpu.so"), reason="oracle/_ref/libtfqmr_ref_gpu.so not built")
+def test_config3_full_size_vs_reference_cuda_build():
+    """BASELINE config 3 at full size (27-point stencil, 32^3 block rows of 32 x 32 complex fp32 blocks, 64 right-hand sides):
+    the reference's own CUDA kernels (unmodified sources, sm_100 build) and this library on the same GPU with the same operands
+    and the same cuRAND shadow vector: plan lists bit-identical, same status, iterations within one, X within 50*tol*max|X|."""
+    import torch
+    from tfqmrgpu_b200 import synthetic
+    n, lm, ln, ncols, tol, maxit = 32, 32, 32, 2, 1e-3, 100
+    sp = synthetic.Stencil27(n, lm, ln, ncols, sigma=8.0, dtype=np.float32, device="cuda")
+    vA = sp.valA_host.numpy().reshape(-1); vB = sp.valB.reshape(-1)
+    with O.quiet_stdout():
+        r = O.ref_gpu().solve(sp.mb, lm, ln, sp.rpA, sp.ciA, vA, sp.rpX, sp.ciX, sp.rpB, sp.ciB, vB, tol, maxit, "c")
+    h = api.Handle()
+    pl = api.BsrsvPlan(h, sp.mb, sp.rpA, sp.ciA, sp.rpX, sp.ciX, sp.rpB, sp.ciB)
+    pl.buffer_size_for(lm, ln, "c"); pl.set_buffer()
+    assert pl.plan_info()["use_tc"] == 1
+    assert np.array_equal(pl.get_v3().reshape(-1), r["v3"])
+    pl.set_matrix("A", None, "n", raw_ptr=sp.valA_host.data_ptr()); pl.set_matrix("B", sp.valB)
+    st = pl.solve(tol, maxit)
+    info = pl.info()
+    X = pl.get_matrix("X", "n", L.LAYOUT_RRRRIIII).reshape(pl.nnzbX, 2, lm, ln)
+    lists = pl.plan_lists()
+    pl.close(); h.close()
+    for k in ("starts", "pairs", "subset", "colindx"):
+        assert np.array_equal(lists[k], r["lists"][k]), k
+    assert st == r["status"] == 0
+    assert abs(info["iterations"] - r["iterations"]) <= 1
+    assert info["residuum"] <= tol and r["residuum"] <= tol
+    assert np.abs(X - r["X"]).max() <= 50*tol*np.abs(r["X"]).max()
+    torch.cuda.empty_cache()
+

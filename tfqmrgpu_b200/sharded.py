@@ -86,6 +86,30 @@ def scatter_shards(shards: list[np.ndarray], sels: list[np.ndarray], nnzbX_globa
     return out
 
 
+class NcclExchange:
+    """The per-iteration exchange of a one-process-per-GPU run (``tfqmrgpux_bsrsv_setShardExchange``): whenever the solver needs
+    the other shards' convergence monitors it calls back, and the ranks all-gather ``world`` blocks of 4 doubles on the solver's
+    stream with NCCL (``torch.distributed``).  Keep the object alive as long as the plan solves."""
+
+    def __init__(self, plan, dist, rank, world, n_rhs_global, device):
+        import torch
+        self.slots = torch.zeros(2*2*world*4, dtype=torch.float64, device=device)
+        self.mine = torch.zeros(4, dtype=torch.float64, device=device)
+        self.calls = 0
+        base = self.slots.data_ptr()
+
+        def hook(ptr, count, stream):
+            off = (ptr - base)//8
+            view = self.slots[off:off + count]
+            ext = torch.cuda.ExternalStream(stream, device=device) if stream else torch.cuda.default_stream(device)
+            with torch.cuda.stream(ext):
+                self.mine.copy_(view[4*rank:4*rank + 4])
+                dist.all_gather_into_tensor(view, self.mine)
+            self.calls += 1
+            return 0
+        plan.set_shard_exchange(rank, world, n_rhs_global, base, hook)
+
+
 class ShardedBsrsv:
     """One rank of a block-column-sharded solve (needs a GPU; uses torch only for device memory and the
     optional NCCL gather)."""
@@ -137,20 +161,7 @@ class ShardedBsrsv:
 
     def _register_exchange(self, dist, rank, world, n_rhs_global):
         """All-gather of the shards' convergence monitors on the solver's stream (the library calls this twice per iteration)."""
-        torch = self.torch
-        self._slots = torch.zeros(2*2*world*4, dtype=torch.float64, device=self.device)
-        self._mine = torch.zeros(4, dtype=torch.float64, device=self.device)
-        base = self._slots.data_ptr()
-
-        def hook(ptr, count, stream):
-            off = (ptr - base)//8
-            view = self._slots[off:off + count]
-            ext = torch.cuda.ExternalStream(stream, device=self.device) if stream else torch.cuda.default_stream(self.device)
-            with torch.cuda.stream(ext):
-                self._mine.copy_(view[4*rank:4*rank + 4])
-                dist.all_gather_into_tensor(view, self._mine)
-            return 0
-        self.plan.set_shard_exchange(rank, world, n_rhs_global, base, hook)
+        self._exchange = NcclExchange(self.plan, dist, rank, world, n_rhs_global, self.device)
 
     def solve(self, threshold, max_iterations):
         if self.plan is None:

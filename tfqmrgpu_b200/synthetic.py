@@ -63,25 +63,33 @@ class Stencil27:
         tdt = torch.float64 if dtype == np.float64 else torch.float32
         self._a_bytes = self.nnzbA*lm*lm*2*(8 if dtype == np.float64 else 4)
         self.valA_host = None
-        if not with_values:      # a rank that receives the replicated operator from a peer needs the index arrays only
+        self._gen = (tdt, pin, torch.device(device), chunk_blocks)
+        if not with_values:      # a rank that uploads only a range of the replicated operator calls values_of() itself
             return
-        self.valA_host = torch.empty((self.nnzbA, lm, lm, 2), dtype=tdt, pin_memory=pin)
-        dev = torch.device(device)
+        self.valA_host = self.values_of(0, self.nnzbA)
+
+    def values_of(self, block0, block1):
+        """Pinned host tensor [block1 - block0, lm, lm, 2] with the A blocks [block0, block1) (the same values whatever the range)."""
+        import torch
+        tdt, pin, dev, chunk_blocks = self._gen
+        lm, sigma, seed = self.lm, self.sigma, self.seed
+        out = torch.empty((block1 - block0, lm, lm, 2), dtype=tdt, pin_memory=pin)
         per = lm*lm*2
         rp_d = torch.from_numpy(self.rpA.astype(np.int64)).to(dev)
         ci_d = torch.from_numpy(self.ciA.astype(np.int64)).to(dev)
         eye = torch.eye(lm, dtype=torch.float64, device=dev)
         ar = torch.arange(per, dtype=torch.int64, device=dev)
-        for b0 in range(0, self.nnzbA, chunk_blocks):
-            b1 = min(self.nnzbA, b0 + chunk_blocks)
+        for b0 in range(block0, block1, chunk_blocks):
+            b1 = min(block1, b0 + chunk_blocks)
             blocks = torch.arange(b0, b1, dtype=torch.int64, device=dev)
             u = hash_uniform_torch(blocks[:, None]*per + ar[None, :], seed).view(b1 - b0, lm, lm, 2)*0.05
             rows = torch.searchsorted(rp_d, blocks, right=True) - 1
             shift = torch.where(rows == ci_d[b0:b1], 27.0 + sigma, -1.0).to(torch.float64)
             u[..., 0] += shift[:, None, None]*eye[None]
-            self.valA_host[b0:b1].copy_(u.to(tdt))
+            out[b0 - block0:b1 - block0].copy_(u.to(tdt))
         if dev.type == "cuda":
             torch.cuda.synchronize(dev)
+        return out
 
     @property
     def a_bytes(self):
