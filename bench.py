@@ -110,6 +110,7 @@ def reference_gpu_same_box(sp, lm, ln, prec, tol, maxit):
         with Quiet():
             out = ref.solve(sp.mb, lm, ln, sp.rpA, sp.ciA, vA, sp.rpX, sp.ciX, sp.rpB, sp.ciB, vB, tol, maxit, prec)
     return {"value": out["flops"]/out["t_solve"]*1e-9, "unit": UNIT, "ms_per_solve": 1e3*out["t_solve"], "iterations": out["iterations"],
+            "createPlan_ms": 1e3*out.get("t_plan", float("nan")),
             "status": int(out["status"]), "residual": out["residuum"],
             "what": "unmodified reference CUDA kernels (gemmNxNf etc.) recompiled for sm_100, same GPU, same workload"}
 
@@ -180,14 +181,21 @@ def _make_plan(torch, api, sp, lm, ln, prec, dev, stream=None, shard=None):
     ncols_global): register the exchange that keeps the reference's GLOBAL iteration / probe rule across the ranks."""
     from tfqmrgpu_b200 import sharded
     h = api.Handle(stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
     pl = api.BsrsvPlan(h, sp.mb, sp.rpA, sp.ciA, sp.rpX, sp.ciX, sp.rpB, sp.ciB)
+    torch.cuda.synchronize(dev)
+    pl.create_plan_ms = 1e3*(time.perf_counter() - t0)          # plan analysis on the device (createPlan), host -> host
     keep = None
     if shard is not None:
         dist, rank, world, ncols_global = shard
         es = 8 if prec == "z" else 4
         pl.set_shard_hints(api.tile_blocks_for(sp.mb*ncols_global, 2*lm*ln*es), ncols_global)
         keep = sharded.NcclExchange(pl, dist, rank, world, ncols_global*ln, dev)
+    t0 = time.perf_counter()
     nbytes = pl.buffer_size_for(lm, ln, prec)
+    torch.cuda.synchronize(dev)
+    pl.configure_ms = 1e3*(time.perf_counter() - t0)            # tiles, units, CTA schedule (bufferSize)
     ws_t = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
     ws_ptr = (ws_t.data_ptr() + 255) & ~255
     pl.set_buffer(ws_ptr, keep_alive=(ws_t, keep))
@@ -234,6 +242,7 @@ def run_ours(args):
     shard = (dist, rank, world, ncols_global) if world > 1 else None
     h, pl, ws_t, base, nbytes = _make_plan(torch, api, sp, lm, ln, prec, dev, shard=shard)
     info = pl.plan_info()
+    create_plan_ms, configure_ms = pl.create_plan_ms, pl.configure_ms
     # every rank uploads ITS row range of A over its own PCIe link (setMatrixPart) and the ranks exchange the converted ranges
     # device to device; the host values of that range only are generated (and pinned) here
     parts = [pl.matrix_part_info(r, world) for r in range(world)]
@@ -431,6 +440,7 @@ def run_ours(args):
                        "iterations_per_solve": iters/args.steps, "iterations_per_solve_min_max_over_ranks": [iters_min, iters_max],
                        "residual_reached": last["residuum"], "status": int(statuses[-1]), "worst_status_over_ranks": worst_status,
                        "workspace_bytes": nbytes, "nnzbA": sp.nnzbA, "nnzbX": nnzbX, "nPairs": nPairs,
+                       "createPlan_ms": create_plan_ms, "bufferSize_ms": configure_ms,
                        "product_kernel": "tcgen05 fp16-pair" if info["use_tc"] else ("dmma" if info["use_dmma"] else "simt")},
             "e2e": {"value": e2e_total/e2e_s*1e-9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "a_distribution": (f"every rank uploads 1/{world} of A over its own PCIe link, converted ranges exchanged with NCCL broadcasts over NVLink"
@@ -478,6 +488,227 @@ def measured_fp64_peak():
         return {"tflops": 37.0, "source": "nominal B200 fp64 (tools/fp64_rate not available)"}
 
 
+# ---- the other BASELINE configurations, same JSON schema (run by `--config N`; the headline stays config 3) ---------------------
+def _ref_bin(name):
+    path = os.path.join(ROOT, "oracle", "_ref", name)
+    return path if os.path.exists(path) else None
+
+
+def run_config1(args):
+    """BASELINE configs[0]: the reference's multiplication plan test/multiplication/plan_unordered.14-287-16 (golden copy under
+    tests/golden), complex fp32 16x16 blocks, bare product Y = A*X (`bench_tfqmrgpu multi`): a step = one product."""
+    import re
+    import tempfile
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orclib as O
+    from tfqmrgpu_b200 import api, problems as P, formats as F, _lib as L
+    g = np.load(os.path.join(ROOT, "tests", "golden", "plan_unordered.npz"))
+    starts, pairs = g["starts"], g["pairs"]
+    nY, nA, nX = [int(v) for v in g["nnz"]]
+    mb, rpA, ciA, rpX, ciX = P.bsr_from_multiplication_plan(starts, pairs, nA)
+    lm = ln = 16
+    h = api.Handle(); pl = api.BsrsvPlan(h, mb, rpA, ciA, rpX, ciX, rpX, ciX)
+    pl.buffer_size_for(lm, ln, "c"); pl.set_buffer()
+    A = O.fill_cos_sin(nA, lm, lm, np.float32); X = O.fill_cos_sin(nX, lm, ln, np.float32)
+    pl.set_matrix("A", A, "t", L.LAYOUT_RRRRIIII); pl.set_matrix("X", X, "n", L.LAYOUT_RRRRIIII)
+    info = pl.plan_info()
+    used_a = len(np.unique(pairs[:, 0]))
+    nbytes = used_a*2*lm*lm*4 + 2*nX*2*lm*ln*4 + 8*len(pairs) + 4*(nY + 1)      # SURVEY.md 8d: 45.14 MB
+    flops = len(pairs)*8*lm*lm*ln
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream_ptr = torch.cuda.current_stream().cuda_stream
+    assert stream_ptr == h.get_stream() or h.get_stream() == 0
+    pl.multiply(max(args.warmup, 3)); torch.cuda.synchronize()
+    sampler = ClockSampler(0); sampler.start(); time.sleep(0.2)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2: every timed product starts cold
+    cold = []
+    for _ in range(args.steps):
+        flush.zero_(); e0.record(); pl.multiply(1); e1.record(); torch.cuda.synchronize(); cold.append(e0.elapsed_time(e1))
+    e0.record(); pl.multiply(200); e1.record(); torch.cuda.synchronize()
+    warm_ms = e0.elapsed_time(e1)/200
+    clocks = sampler.stop()
+    cold_ms = float(np.median(cold))
+    Y = pl.get_vector("Y", "n", L.LAYOUT_RRRRIIII).reshape(nX, 2, lm, ln)
+    # end to end: X host -> device, product, Y device -> host (A resident like in the harness)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pl.set_matrix("X", X, "n", L.LAYOUT_RRRRIIII); pl.multiply(1); pl.get_vector("Y", "n", L.LAYOUT_RRRRIIII)
+    e2e_ms = 1e3*(time.perf_counter() - t0)/args.steps
+    pl.close(); h.close()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    line = {"metric": "bsr_spmm_time", "value": 1e3*cold_ms, "unit": "us", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": cold_ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "plan_unordered.14-287-16: 4490 Y blocks, 50526 pairs, complex fp32 16x16 blocks, cos/sin fill (bench_tfqmrgpu multi)",
+                       "l2": "working set 45 MB < 126 MB L2: flushed before every timed product (value), warm figure beside it",
+                       "warm_us": 1e3*warm_ms, "warm_tflops": flops/warm_ms*1e-9, "units": info["nUnits"], "entries": info["nEntries"],
+                       "product_kernel": "tcgen05 fp16-pair" if info["use_tc"] else "simt"},
+            "e2e": {"value": 1e3*e2e_ms, "unit": "us", "h2d_bytes_per_step": int(X.nbytes), "d2h_bytes_per_step": int(Y.nbytes)},
+            "gpu_launches": 3*args.steps,
+            "roofline": {"bound": "hbm", "kernel": "spmm (block-sparse product Y=A*X)", "achieved": nbytes/cold_ms*1e-6, "peak": peak, "unit": "GB/s",
+                         "frac": nbytes/cold_ms*1e-6/peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                         "avg_launch_ms": cold_ms, "algorithmic_bytes_per_launch": nbytes, "achieved_tflops": flops/cold_ms*1e-9,
+                         "note": "148 persistent CTAs share 1663 units of 6-14 entries (2 KB A blocks): the launch is latency-bound "
+                                 "(pipeline fill + one epilogue per unit), not HBM-bound; includes the X operand conversion"},
+            "clocks": clocks}
+    if not args.no_cpu:
+        t0 = time.perf_counter()
+        Yo = O.multiply(A, X, starts, pairs.reshape(-1), lm, ln, nthreads=os.cpu_count())
+        tcpu = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 1e6*tcpu, "unit": "us", "cores": os.cpu_count(), "kind": "port",
+                                "sample": "the whole product once: restatement of the harness's OpenMP check loop (bench_tfqmrgpu.cu:358-404)"}
+        line["config"]["maxdev_vs_cpu"] = float(np.abs(Y - Yo).max())
+        exe = _ref_bin("bench_tfqmrgpu_ref")
+        if exe and not args.no_ref_gpu:      # the reference's own kernel (gemmNxNf, sm_100 build) on this GPU: `multi <plan> f 100 1 16 16`
+            with tempfile.TemporaryDirectory() as td:
+                plan = os.path.join(td, "plan_unordered.14-287-16")
+                F.write_multiplication_plan(plan, starts, pairs, nA, nX)
+                out = subprocess.run([exe, "multi", plan, "f", "100", "1", "16", "16"], capture_output=True, text=True, timeout=600)
+            m = re.search(r"# GPU performance \(lm,ln,tune\)=\( *16, *16,\d\) is +([0-9.]+) G[fF]lop/sec", out.stdout)
+            line["reference_gpu"] = ({"value": flops/float(m.group(1))*1e-3, "unit": "us", "gflops": float(m.group(1)),
+                                      "what": "unmodified bench_tfqmrgpu multi (reference kernels, sm_100 build), warm, same GPU"}
+                                     if m else {"error": out.stdout[-300:]})
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_config2(args):
+    """BASELINE configs[1]: full tfQMR solve of FD_problem.xml (generate_FD_example defaults), complex fp64, 1 GPU: a step = one solve."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orclib as O
+    from tfqmrgpu_b200 import api, problems as P
+    prob = P.read_xml(os.path.join(ROOT, "tests", "golden", "FD_problem.xml"))
+    vA = P.interleave(prob.A.val, np.float64); vB = P.interleave(prob.B.val, np.float64)
+    h = api.Handle()
+    pl = api.BsrsvPlan(h, prob.mb, prob.A.rowptr, prob.A.colind, prob.X.rowptr, prob.X.colind, prob.B.rowptr, prob.B.colind)
+    pl.buffer_size_for(prob.lm, prob.ln, "z"); pl.set_buffer()
+    pl.set_matrix("A", vA, "t"); pl.set_matrix("B", vB, "t")
+    for _ in range(max(args.warmup, 3)):
+        st = pl.solve(prob.tolerance, 2000)
+    sampler = ClockSampler(0); sampler.start(); time.sleep(0.2)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        st = pl.solve(prob.tolerance, 2000)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)/args.steps
+    clocks = sampler.stop()
+    info = pl.info(); stats = pl.solve_stats()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pl.set_matrix("A", vA, "t"); pl.set_matrix("B", vB, "t"); pl.solve(prob.tolerance, 2000); X = pl.get_matrix("X")
+    e2e_ms = 1e3*(time.perf_counter() - t0)/args.steps
+    pl.close(); h.close()
+    line = {"metric": "tfqmr_solve_time", "value": ms, "unit": "ms", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "FD_problem.xml (generate_FD_example defaults): 171 block rows of 8x8, 1557 A blocks, 1 RHS block column, complex fp64, tol 1e-9",
+                       "l2": "working set 3 MB, L2-resident by nature (launch-latency-bound; no flush: a flush would time the flush)",
+                       "iterations": info["iterations"], "status": int(st), "residual": info["residuum"], "gflops": info["flops"]/ms*1e-6},
+            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(vA.nbytes + vB.nbytes), "d2h_bytes_per_step": int(X.nbytes)},
+            "gpu_launches": int(stats["launches"]),
+            "roofline": {"bound": "hbm", "kernel": "whole solve (latency-bound: ~10 MB per iteration)", "achieved": None, "peak": None, "unit": "GB/s",
+                         "frac": None, "traffic": None, "note": "the roofline fraction is not meaningful for this 3 MB problem (SURVEY.md 8d): "
+                                                                 "time = iterations x (kernel launches of one CUDA graph)"},
+            "clocks": clocks}
+    if not args.no_cpu:
+        for name, ref in (("cpu_baseline", O.ref_cpu()), ("reference_gpu", None if args.no_ref_gpu else O.ref_gpu())):
+            if ref is None:
+                continue
+            tr = []
+            for _ in range(3):
+                with Quiet():
+                    r = ref.solve(prob.mb, prob.lm, prob.ln, prob.A.rowptr, prob.A.colind, vA, prob.X.rowptr, prob.X.colind,
+                                  prob.B.rowptr, prob.B.colind, vB, prob.tolerance, 2000, "z", transA="t", trans_b="t")
+                tr.append(r["t_solve"])
+            entry = {"value": 1e3*float(np.median(tr)), "unit": "ms", "iterations": r["iterations"], "status": int(r["status"])}
+            if name == "cpu_baseline":
+                entry.update({"cores": 1, "kind": "reference", "sample": "the whole solve (serial reference CPU build), median of 3"})
+            else:
+                entry["what"] = "unmodified reference CUDA build (sm_100), same GPU, median of 3"
+            line[name] = entry
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_config5(args):
+    """BASELINE configs[4]: sweep of block size x right-hand-side count x precision on the 27-point block stencil; the cases are
+    dealt round robin to the ranks (independent problems, no collective), rank 0 prints all rows.  fp64 at tol 1e-9 (sigma 1);
+    fp32 cannot reach 1e-9 (its floor is ~1e-4): tol 1e-3 (sigma 8), stated per row."""
+    import torch
+    import torch.distributed as dist
+    from tfqmrgpu_b200 import api, synthetic
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sizes = [(4, 4), (4, 5), (4, 8), (4, 32), (8, 8), (8, 9), (8, 10), (8, 32), (8, 64), (16, 16), (16, 32), (16, 64), (32, 32), (32, 64), (64, 64)]
+    n = args.sweep_n
+    cases = [(lm, ln, rhs, prec) for (lm, ln) in sizes for rhs in args.sweep_rhs for prec in ("c", "z") if rhs >= ln or rhs == min(args.sweep_rhs)]
+    rows = []
+    t_all0 = time.perf_counter()
+    for k, (lm, ln, rhs, prec) in enumerate(cases):
+        if k % world != rank:
+            continue
+        ncols = max(1, rhs//ln)
+        dt, sigma, tol, es = (np.float32, 8.0, 1e-3, 4) if prec == "c" else (np.float64, 1.0, 1e-9, 8)
+        if 8.5*n**3*ncols*2*lm*ln*es + 27*n**3*2*lm*lm*es > 150e9:
+            continue
+        sp = synthetic.Stencil27(n, lm, ln, ncols, sigma=sigma, dtype=dt, device=dev)
+        h = api.Handle(); pl = api.BsrsvPlan(h, sp.mb, sp.rpA, sp.ciA, sp.rpX, sp.ciX, sp.rpB, sp.ciB)
+        pl.buffer_size_for(lm, ln, prec); pl.set_buffer()
+        pl.set_matrix("A", None, "n", raw_ptr=sp.valA_host.data_ptr()); pl.set_matrix("B", sp.valB)
+        info = pl.plan_info()
+        for _ in range(2):
+            st = pl.solve(tol, 200)
+        pl.set_profiling(True); pl.solve(tol, 200); prof = pl.solve_profile(); pl.set_profiling(False)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); st = pl.solve(tol, 200); e1.record(); torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1); res = pl.info()
+        sp_ms = prof["spmm_ms"]/max(prof["spmm_launches"], 1)
+        nP = info["nPairs"]
+        rows.append(dict(lm=lm, ln=ln, rhs=ncols*ln, prec=prec, tol=tol, status=int(st), iterations=res["iterations"], residual=res["residuum"],
+                         solve_ms=ms, gflops=res["flops"]/ms*1e-6, spmm_us=1e3*sp_ms, spmm_gflops=nP*8*lm*lm*ln/sp_ms*1e-6 if sp_ms else 0,
+                         kernel="dmma" if info["use_dmma"] else ("tcgen05" if info["use_tc"] else ("simt-small" if info.get("use_small") else "simt")), rank=rank))
+        pl.close(); h.close(); del sp
+        torch.cuda.empty_cache()
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t_all0
+    if world > 1:
+        gathered = [None]*world
+        dist.all_gather_object(gathered, rows)
+        rows = [r for part in gathered for r in part]
+        t = torch.tensor([wall], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); wall = float(t.item())
+    if rank == 0:
+        rows.sort(key=lambda r: (r["lm"], r["ln"], r["rhs"], r["prec"]))
+        total_flops = sum(r["gflops"]*r["solve_ms"]*1e-3 for r in rows)       # GFLOP of one timed solve per case
+        busy = sum(r["solve_ms"] for r in rows)*1e-3
+        line = {"metric": "tfqmr_sweep_throughput", "value": total_flops/max(busy/world, 1e-9), "unit": "GFLOP/s", "n_gpus": world, "steps": 1, "warmup": 3,
+                "ms_per_step": 1e3*busy/world, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+                "config": {"workload": f"sweep: 15 block sizes x RHS {list(args.sweep_rhs)} x (fp32 tol 1e-3 | fp64 tol 1e-9) on stencil27 n={n}^3, "
+                                       f"{len(rows)} cases dealt round robin to {world} GPU(s)", "wall_s_incl_setup": wall,
+                           "all_converged": all(r["status"] == 0 for r in rows), "rows": rows},
+                "e2e": None, "gpu_launches": None, "roofline": None, "clocks": None}
+        if not args.no_cpu and world >= 1:
+            try:
+                r = cpu_reference_sample(8, 8, 8, "z", 1e-9, 200, repeats=1)
+                line["cpu_baseline"] = {"value": r["flops"]/r["times"][0]*1e-9, "unit": UNIT, "cores": 1, "kind": r["kind"],
+                                        "sample": r["sample"].replace("32x32", "8x8") + " (one case of the sweep)"}
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "kind": "unavailable", "sample": repr(e)[:200]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -496,9 +727,24 @@ def main():
     ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3, 4, 5], help="BASELINE.json configuration (1-based); 3 is the headline")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline (and reference_gpu) legs")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the informational same-box run of the reference's CUDA kernels")
+    ap.add_argument("--sweep-n", type=int, default=12, help="config 5: grid edge of the sweep's stencil")
+    ap.add_argument("--sweep-rhs", type=int, nargs="+", default=[64, 512], help="config 5: right-hand-side counts (BASELINE: 8 ... 4096)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == 1:
+        return run_config1(args)
+    if args.config == 2:
+        return run_config2(args)
+    if args.config == 5:
+        return run_config5(args)
+    if args.config == 4:
+        # BASELINE configs[3]: the stencil in complex fp64 with 1024 right-hand-side columns (32 block columns of 32; read as in
+        # SURVEY.md 8d) sharded over the GPUs: strong scaling by construction (the per-GPU share shrinks with N)
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        args.precision, args.sigma, args.tol, args.strong_rhs = "z", 1.0, 1e-9, 0
+        args.ncols = max(1, 32//world)
+        os.environ.setdefault("TFQMRGPU_BENCH_NO_PIPELINE", "1")      # one workspace of 8 fp64 vectors + A per GPU is the budget
     return run_ours(args)
 
 

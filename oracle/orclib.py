@@ -249,8 +249,10 @@ class RefLib:
         h = C.c_void_p(); assert lib.tfqmrgpuCreateHandle(C.byref(h)) == 0
         plan = C.c_void_p()
         a = [np.ascontiguousarray(v, np.int32) for v in (rpA, ciA, rpX, ciX, rpB, ciB)]
+        t_plan0 = time.perf_counter()
         st = lib.tfqmrgpu_bsrsv_createPlan(h, C.byref(plan), mb, a[0], len(ciA), a[1], a[2], len(ciX), a[3],
                                            a[4], len(ciB), a[5], index_offset, 0)
+        t_plan = time.perf_counter() - t_plan0
         assert st == 0, st
         size = C.c_size_t()
         st = lib.tfqmrgpu_bsrsv_bufferSize(h, plan, lm, lm, ln, ln, precision.encode(), C.byref(size))
@@ -288,7 +290,7 @@ class RefLib:
             lib.tfqmrgpuDestroyWorkspace(buf)
         lib.tfqmrgpuDestroyHandle(h)
         return dict(status=status, X=Xint, iterations=it.value, residuum=res.value, flops=fl.value,
-                    buffer_size=size.value, v3=v3_used, lists=lists, t_solve=t_solve)
+                    buffer_size=size.value, v3=v3_used, lists=lists, t_solve=t_solve, t_plan=t_plan)
 
 
 _ref_cpu = None
