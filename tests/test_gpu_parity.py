@@ -522,7 +522,7 @@ def test_full_size_properties(prec, ncol, sigma, tol, max_it):
     torch.cuda.empty_cache()
 
 
-# ---- tensor-core product (spmm_tc.cu): selection, accuracy statement, SIMT fallback switch ------------------
+# ---- tensor-core product (spmm_tc16p.cu, spmm_tc16.cu): selection, accuracy statement, SIMT fallback switch ------------------
 def _stencil_product(ncol, fill_seed=1):
     rp, ci = P.stencil27_pattern(4)
     rpX = (ncol*np.arange(65)).astype(np.int32); ciX = np.tile(np.arange(ncol, dtype=np.int32), 64)
@@ -753,7 +753,7 @@ def test_fortran_shims_full_solve():
 @pytest.mark.parametrize("lmln,level,expect", [((16, 16), "1", 1), ((16, 64), "1", 1), ((64, 64), "1", 1), ((64, 64), "0", 0)],
                          ids=["16x16", "16x64", "64x64", "64x64-simt"])
 def test_tensor_core_product_other_block_sizes(lmln, level, expect, monkeypatch):
-    """tcgen05 path for LM = 16 and LM = 64 (multi-pass accumulation, see spmm_tc.cu): product within 1e-4 absolute of the
+    """tcgen05 path for LM = 16 and LM = 64 (accumulation segments, see spmm_tc16p.cu): product within 1e-4 absolute of the
     fp32 oracle (bench_tfqmrgpu.cu:414) and within 2e-6 * sum|terms| of an fp64 evaluation."""
     lm, ln = lmln
     monkeypatch.setenv("TFQMRGPU_TENSOR", level)

@@ -294,7 +294,7 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_setMatrix(tfqmrgpuHandle_t handle, tfqmrgpuBsrsv
         size_t const chunkBytes = size_t(256) << 20;
         // after the layout conversion of a chunk: block maxima for the row scales of the fp16-pair operand (xop.cu)
         auto converted = [&](uint32_t b0, uint32_t nb) -> tfqmrgpuStatus_t {
-            tfqmrgpuStatus_t const cst = convert_inplace(p, dst + size_t(b0)*blockBytes, nb, p.LM, p.LM, is_double, layout, trans, scal_imag, stream, p.use_tc);
+            tfqmrgpuStatus_t const cst = convert_inplace(p, dst + size_t(b0)*blockBytes, nb, p.LM, p.LM, is_double, layout, trans, scal_imag, stream);
             if (cst || !p.use_tc16) return cst;
             return launch_aop_blockmax(p, b0, nb, stream);
         };
@@ -486,7 +486,7 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getPlanInfo(tfqmrgpuBsrsvPlan_t plan, int64_t i
     if (nullptr == plan || nullptr == info) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     Plan const &p = *P(plan);
     int64_t const v[16] = {p.nnzbX, p.nnzbB, p.nnzbA, int64_t(p.nCols), int64_t(p.nPairs), p.LM, p.LN, p.precision,
-                           int64_t(p.nTiles), int64_t(p.nUnits), int64_t(p.gmax), int64_t(p.nEntries), p.mb, int64_t(p.use_tc || p.use_tc16), int64_t(p.use_dmma), int64_t(p.use_small)};
+                           int64_t(p.nTiles), int64_t(p.nUnits), int64_t(p.gmax), int64_t(p.nEntries), p.mb, int64_t(p.use_tc16), int64_t(p.use_dmma), int64_t(p.use_small)};
     std::memcpy(info, v, sizeof(v));
     return TFQMRGPU_STATUS_SUCCESS;
 }
@@ -678,7 +678,7 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_setMatrixPart(tfqmrgpuHandle_t handle, tfqmrgpu
     char *const dst = p.pBuffer + info[0];
     uint32_t const b0 = uint32_t(info[4]), nb = uint32_t(info[5]);
     TFQ_CUDA(cudaMemcpyAsync(dst, valPart, size_t(info[1]), cudaMemcpyHostToDevice, stream));
-    st = convert_inplace(p, dst, nb, p.LM, p.LM, is_double, layout, trans, scal_imag, stream, p.use_tc);
+    st = convert_inplace(p, dst, nb, p.LM, p.LM, is_double, layout, trans, scal_imag, stream);
     if (TFQMRGPU_STATUS_SUCCESS == st && p.use_tc16) st = launch_aop_blockmax(p, b0, nb, stream);
     if (TFQMRGPU_STATUS_SUCCESS == st && p.use_tc16) st = launch_aop_convert_rows(p, row0, row1, stream);
     return st;

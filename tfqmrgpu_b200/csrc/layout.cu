@@ -38,7 +38,7 @@ HostIndex host_index(int layout, int rows, int cols, bool trans) {
 // map = perm (caller index -> storage index) or identity when perm == nullptr
 template <typename real_t>
 __global__ void convert_kernel(real_t *dst, real_t const *src, uint32_t const *__restrict__ perm,
-                               int rows, int cols, HostIndex h, real_t scal_imag, bool to_internal, bool umma_kmajor)
+                               int rows, int cols, HostIndex h, real_t scal_imag, bool to_internal)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     real_t *const tmp = reinterpret_cast<real_t*>(smem_raw);
@@ -54,10 +54,7 @@ __global__ void convert_kernel(real_t *dst, real_t const *src, uint32_t const *_
         if (to_internal) {
             uint32_t const c = q / plane, ij = q - c*plane, i = ij / cols, j = ij - i*cols;
             real_t const v = tmp[h.Ni*i + h.Nj*j + h.Nc*c];
-            // umma_kmajor (square A blocks of the tensor-core product, spmm_tc.cu): element (c, k = i, n = c*rows + j)
-            // goes to [k/4][n][k%4], the K-major no-swizzle operand layout of tcgen05.mma, ready for a bulk copy
-            uint32_t const dq = umma_kmajor ? ((i >> 2)*(8u*rows) + (c*rows + j)*4u + (i & 3u)) : q;
-            d[dq] = c ? scal_imag*v : v;
+            d[q] = c ? scal_imag*v : v;
         } else {
             // decode the host position q -> (i, j, c): invert h by trying the three stride orders
             uint32_t c, i, j;
@@ -83,7 +80,7 @@ __global__ void permute_blocks_f32(float *dst, float const *src, uint32_t const 
 
 template <typename real_t>
 tfqmrgpuStatus_t run_convert(void *dst, void const *src, uint32_t const *perm, uint32_t nnzb, int rows, int cols,
-                             int layout, bool trans, double scal_imag, bool to_internal, cudaStream_t stream, bool umma_kmajor = false)
+                             int layout, bool trans, double scal_imag, bool to_internal, cudaStream_t stream)
 {
     if (nnzb < 1) return TFQMRGPU_STATUS_SUCCESS;
     size_t const smem = 2*size_t(rows)*cols*sizeof(real_t);
@@ -91,7 +88,7 @@ tfqmrgpuStatus_t run_convert(void *dst, void const *src, uint32_t const *perm, u
     if (smem > 48*1024) TFQ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int const threads = int(std::min<size_t>(256, ((2*size_t(rows)*cols + 31)/32)*32));
     kernel<<<nnzb, threads, smem, stream>>>(static_cast<real_t*>(dst), static_cast<real_t const*>(src), perm, rows, cols,
-                                           host_index(layout, rows, cols, trans), real_t(scal_imag), to_internal, umma_kmajor);
+                                           host_index(layout, rows, cols, trans), real_t(scal_imag), to_internal);
     TFQ_CUDA(cudaGetLastError());
     return TFQMRGPU_STATUS_SUCCESS;
 }
@@ -99,10 +96,10 @@ tfqmrgpuStatus_t run_convert(void *dst, void const *src, uint32_t const *perm, u
 } // namespace
 
 tfqmrgpuStatus_t convert_inplace(Plan const &, void *blocks, uint32_t nnzb, int rows, int cols, bool is_double,
-                                 int layout, bool trans, double scal_imag, cudaStream_t stream, bool umma_kmajor)
+                                 int layout, bool trans, double scal_imag, cudaStream_t stream)
 {
-    return is_double ? run_convert<double>(blocks, blocks, nullptr, nnzb, rows, cols, layout, trans, scal_imag, true, stream, umma_kmajor)
-                     : run_convert<float >(blocks, blocks, nullptr, nnzb, rows, cols, layout, trans, scal_imag, true, stream, umma_kmajor);
+    return is_double ? run_convert<double>(blocks, blocks, nullptr, nnzb, rows, cols, layout, trans, scal_imag, true, stream)
+                     : run_convert<float >(blocks, blocks, nullptr, nnzb, rows, cols, layout, trans, scal_imag, true, stream);
 }
 
 tfqmrgpuStatus_t convert_permuted(Plan const &p, void *dst, void const *src, uint32_t nnzb, int rows, int cols,

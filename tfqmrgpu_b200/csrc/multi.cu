@@ -296,7 +296,7 @@ tfqmrgpuStatus_t multi_set_matrix(Plan &p, char v, void const *val, char precisi
             char *const dst = sp.pBuffer + sp.off_A + size_t(b0)*blockBytes;
             if (cudaSuccess != cudaMemcpyAsync(dst, static_cast<char const*>(val) + size_t(b0)*blockBytes, size_t(b1 - b0)*blockBytes,
                                                cudaMemcpyHostToDevice, sh.stream)) { status[s] = TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED); return; }
-            tfqmrgpuStatus_t st = convert_inplace(sp, dst, b1 - b0, p.LM, p.LM, is_double, layout, trans, scal_imag, sh.stream, sp.use_tc);
+            tfqmrgpuStatus_t st = convert_inplace(sp, dst, b1 - b0, p.LM, p.LM, is_double, layout, trans, scal_imag, sh.stream);
             if (TFQMRGPU_STATUS_SUCCESS == st && sp.use_tc16) st = launch_aop_blockmax(sp, b0, b1 - b0, sh.stream);
             if (TFQMRGPU_STATUS_SUCCESS == st && sp.use_tc16) st = launch_aop_convert_rows(sp, sh.a_row0, sh.a_row1, sh.stream);
             status[s] = st;

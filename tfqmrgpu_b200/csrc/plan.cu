@@ -454,12 +454,10 @@ tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, ch
         g = std::min(g, p.maxColsPerRow);
         // keep one pipeline stage (A block + g X blocks, possibly k-chunked) reasonable: <= 48 KiB at 4 k-rows
         while (g > 1 && 2*4*(size_t(LM) + size_t(g)*LN)*s > 48*1024) --g;
-        // TFQMRGPU_TENSOR: 0 SIMT kernels only, 1 (default) fp16-pair tcgen05 product / DMMA, 2 the earlier 3xTF32 tcgen05 product
+        // TFQMRGPU_TENSOR: 0 SIMT kernels only, 1 (default) fp16-pair tcgen05 product (complex fp32) / DMMA (complex fp64)
         char const *env = std::getenv("TFQMRGPU_TENSOR");
         int const level = env ? std::atoi(env) : 1;
         p.use_tc16 = spmm_tc16_supported(LM, LN, precision, level);
-        p.use_tc = !p.use_tc16 && spmm_tc_supported(LM, LN, precision, (level >= 2) ? 1 : 0);
-        if (p.use_tc) g = spmm_tc_columns_per_unit(LN);   // 128 MMA rows = g * 2 * LN
         if (p.use_tc16) g = spmm_tc16_columns_per_unit(LM, LN);
         p.use_dmma = spmm_dmma_supported(LM, LN, precision) && (level >= 1);
         if (p.use_dmma) g = std::min(spmm_dmma_columns_per_unit(LM, LN), std::max(1, p.maxColsPerRow));

@@ -500,7 +500,6 @@ tfqmrgpuStatus_t launch_spmm(Plan const &p, void *y, void const *x, int expect, 
         tfqmrgpuStatus_t const st = skip_xop ? TFQMRGPU_STATUS_SUCCESS : launch_xop(p, x, expect, stream);
         return st ? st : (p.tc_planar ? launch_spmm_tc16p(p, y, expect, stream) : launch_spmm_tc16(p, y, expect, stream));
     }
-    if (p.use_tc) return launch_spmm_tc(p, y, x, expect, stream);
     if (p.use_dmma) return launch_spmm_dmma(p, y, x, expect, stream);
     switch (p.LM*1000 + p.LN) {
 #define TFQ_CASE(LM, LN) case LM*1000 + LN: return launch_sized<LM, LN>(p, y, x, expect, stream);

@@ -46,8 +46,19 @@ __device__ __forceinline__ bool mbar_try_wait_d(uint64_t *bar, unsigned parity) 
                  : "=r"(ok) : "r"(smem_u32d(bar)), "r"(parity) : "memory");
     return 0 != ok;
 }
+// bounded by wall time (%globaltimer, 4 s): a pipeline that never signals is a bug and must end the launch with an error instead of
+// hanging the stream; a legitimately slow stage (profiler replay, managed memory migrating) is waited for
 __device__ __forceinline__ void mbar_wait_d(uint64_t *bar, unsigned parity) {
-    for (uint32_t spins = 0; !mbar_try_wait_d(bar, parity); ++spins) if (spins > (1u << 24)) __trap();
+    if (mbar_try_wait_d(bar, parity)) return;
+    uint64_t t0 = 0;
+    for (uint32_t spins = 1; !mbar_try_wait_d(bar, parity); ++spins) {
+        if (0 == (spins & 0xfffu)) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (0 == t0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
+    }
 }
 __device__ __forceinline__ void mbar_arrive_d(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32d(bar)) : "memory");

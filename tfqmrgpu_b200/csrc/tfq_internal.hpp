@@ -92,7 +92,6 @@ struct Plan {
     uint32_t nUnits = 0, gmax = 1; uint64_t nEntries = 0;
     bool use_tc16 = false;            // block-sparse product on the tensor cores, fp16 operand pairs (spmm_tc16.cu, xop.cu)
     bool tc_planar = false;           // ... in the planar form (spmm_tc16p.cu: four real products, the fast kernel for short rows)
-    bool use_tc = false;              // the earlier 3xTF32 tensor-core product (spmm_tc.cu; TFQMRGPU_TENSOR=2)
     bool use_dmma = false;            // complex fp64 product on the FP64 tensor pipe (spmm_dmma.cu)
     Exchange exch;
     struct MultiPlan *multi = nullptr;       // in-process multi-GPU plan (multi.cu): this Plan is then only the global analysis
@@ -173,10 +172,6 @@ tfqmrgpuStatus_t multi_rhs_status(Plan &p, int8_t *statusHost);
 // ---- kernels' host launchers --------------------------------------------------------------------
 // block-sparse product y = A*x on storage-ordered vectors; gate: run only if ctl->state == expect (expect < 0: always)
 tfqmrgpuStatus_t launch_spmm(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream);
-// tcgen05 3xTF32 variant (spmm_tc.cu): complex fp32, LM in {16, 32, 64}; off with TFQMRGPU_TENSOR=0
-bool spmm_tc_supported(int LM, int LN, char precision, int level);
-int  spmm_tc_columns_per_unit(int LN);
-tfqmrgpuStatus_t launch_spmm_tc(Plan const &p, void *y, void const *x, int expect, cudaStream_t stream);
 // fp16-pair tensor-core variant (spmm_tc16.cu, the default for complex fp32 with LM, LN in {16, 32, 64}) and its operands (xop.cu)
 bool spmm_tc16_supported(int LM, int LN, char precision, int level);
 int  spmm_tc16_columns_per_unit(int LM, int LN);
@@ -205,7 +200,7 @@ tfqmrgpuStatus_t launch_vecop_xop(Plan const &p, int op, cudaStream_t stream);
 tfqmrgpuStatus_t launch_add_rhs(Plan const &p, void *v, double scal, int expect, cudaStream_t stream);
 // host layout <-> internal layout (layout.cu)
 tfqmrgpuStatus_t convert_inplace(Plan const &p, void *blocks, uint32_t nnzb, int rows, int cols, bool is_double,
-                                 int layout, bool trans, double scal_imag, cudaStream_t stream, bool umma_kmajor = false);
+                                 int layout, bool trans, double scal_imag, cudaStream_t stream);
 tfqmrgpuStatus_t convert_permuted(Plan const &p, void *dst, void const *src, uint32_t nnzb, int rows, int cols,
                                   bool is_double, int layout, bool trans, double scal_imag, bool to_internal,
                                   cudaStream_t stream);

@@ -1,4 +1,4 @@
-// Microbenchmark (dev tool, not part of the library): issue rate of tcgen05.mma on B200 for the shapes spmm_tc.cu uses.
+// Microbenchmark (dev tool, not part of the library): issue rate of tcgen05.mma on B200 for the shapes of the round-1 3xTF32 product (kept as the measurement behind DESIGN.md: one MMA per ~54 cycles for N <= 64).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/mma_rate tools/mma_rate.cu && tools/mma_rate
 // One CTA per SM, one elected lane issues `reps` MMAs back to back on static operands and commits to an mbarrier;
 // clock64 around issue+completion gives cycles per MMA.  kind: 0 = tf32 (K=8), 1 = bf16 (K=16).  mode: 0 = SS, 1 = TS.
