@@ -558,7 +558,7 @@ def run_config1(args):
                          "frac": nbytes/cold_ms*1e-6/peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
                          "avg_launch_ms": cold_ms, "algorithmic_bytes_per_launch": nbytes, "achieved_tflops": flops/cold_ms*1e-9,
                          "note": "148 persistent CTAs share 1663 units of 6-14 entries (2 KB A blocks): the launch is latency-bound "
-                                 "(pipeline fill + one epilogue per unit), not HBM-bound; includes the X operand conversion"},
+                                 "(pipeline fill + one epilogue per unit), not HBM-bound; the X operand is converted with the upload of X (setMatrix), the timed launch is the product alone"},
             "clocks": clocks}
     if not args.no_cpu:
         t0 = time.perf_counter()

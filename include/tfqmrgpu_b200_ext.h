@@ -90,6 +90,11 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getSolveProfile(tfqmrgpuBsrsvPlan_t plan, doubl
 typedef int32_t (*tfqmrgpuxOperator_t)(void *ctx, void *y, void const *x, int32_t const *state, int32_t expect, cudaStream_t stream);
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_setOperator(tfqmrgpuBsrsvPlan_t plan, tfqmrgpuxOperator_t op, void *ctx);
 
+/* The right-hand sides of the reference's `rhs_trivial` mode (tfqmrgpu_core.hxx:27,140-147: "columns of the unit matrix"): every
+ * B block becomes the unit block (Re b[j mod LM][j] = 1).  Instead of setMatrix('B'); the reference offers this only to C++ callers
+ * of its solve() template. */
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setRhsTrivial(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan);
+
 /* ---- several GPUs: the independent right-hand-side block columns of X/B are sharded, A is replicated --------
  *
  * (1) One process, several devices - for C, Fortran and Julia callers.  Call setDevices after createPlan and before

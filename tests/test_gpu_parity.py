@@ -771,3 +771,29 @@ def test_tensor_core_product_other_block_sizes(lmln, level, expect, monkeypatch)
     Y64 = O.multiply(A.astype(np.float64), X.astype(np.float64), lists["starts"], lists["pairs"], lm, ln)
     assert np.abs(Y - Y32).max() <= 1e-4
     assert np.abs(Y - Y64).max() <= 2e-6*prob.mb*lm*4
+
+
+@pytest.mark.parametrize("lm,ln,prec,tol", [(4, 5, "z", 1e-9), (8, 8, "z", 1e-9), (16, 32, "c", 1e-4)], ids=["4x5z", "8x8z", "16x32c"])
+def test_rhs_trivial_equals_uploaded_unit_blocks(lm, ln, prec, tol):
+    """tfqmrgpux_bsrsv_setRhsTrivial: the right-hand sides of the reference's rhs_trivial mode (core.hxx:140-147, set_unit_blocks
+    linalg.hxx:432-455: Re b[j mod LM][j] = 1) without an upload - bit-identical to uploading those blocks with setMatrix('B')."""
+    prob = P.random_system(12, lm, ln, seed=3*lm + ln, unsorted=True)
+    dt = np.float64 if prec == "z" else np.float32
+    vA = P.interleave(prob.A.val, dt)
+    unit = np.zeros((prob.B.nnzb, 2, lm, ln), dt)
+    for j in range(ln):
+        unit[:, 0, j % lm, j] = 1
+    out = []
+    for trivial in (False, True):
+        h, pl = _open(prob)
+        pl.buffer_size_for(lm, ln, prec); pl.set_buffer()
+        pl.set_matrix("A", vA)
+        if trivial:
+            pl.set_rhs_trivial()
+        else:
+            pl.set_matrix("B", unit, "n", L.LAYOUT_RRRRIIII)
+        st = pl.solve(tol, 200)
+        out.append((st, pl.info()["iterations"], pl.get_matrix("X").copy()))
+        pl.close(); h.close()
+    assert out[0][0] == out[1][0] == 0 and out[0][1] == out[1][1] and np.array_equal(out[0][2], out[1][2])
+

@@ -283,6 +283,10 @@ class BsrsvPlan:
                                                      trans.encode(), layout, int(part), int(n_parts), info), "setMatrixPart")
         return dict(off=int(info[0]), length=int(info[1]), scale_off=int(info[2]), scale_length=int(info[3]), block0=int(info[4]), nblocks=int(info[5]))
 
+    def set_rhs_trivial(self):
+        """B := unit blocks (the reference's rhs_trivial right-hand sides) instead of set_matrix('B', ...)."""
+        _check(self.lib.tfqmrgpux_bsrsv_setRhsTrivial(self.handle.h, self.plan), "setRhsTrivial")
+
     def set_shard_hints(self, tile_blocks: int, max_cols_per_row: int = 0):
         _check(self.lib.tfqmrgpux_bsrsv_setShardHints(self.plan, int(tile_blocks), int(max_cols_per_row)), "setShardHints")
 

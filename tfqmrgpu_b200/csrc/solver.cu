@@ -177,6 +177,7 @@ tfqmrgpuStatus_t solve_begin(Plan &p, cudaStream_t stream, double tolerance, int
     TFQ_CUDA(cudaMemsetAsync(p.pBuffer + p.off_v[1], 0, (p.off_v[9] + p.vecBytes) - p.off_v[1], stream));
     if (p.use_tc16) TFQ_CUDA(cudaMemsetAsync(p.pBuffer + p.off_mx, 0, 3*size_t(p.nCols)*p.LN*sizeof(float), stream));   // max|v6| = 0
     p.exch.parity = 0;
+    p.xop_of_x = false;             // the iterations overwrite the tensor-core operand (and X itself)
 
     tfqmrgpuStatus_t st;
     st = launch_add_rhs(p, p.pBuffer + p.off_v[5], 1.0, -1, stream);       // v5 := b        (core.hxx:153)

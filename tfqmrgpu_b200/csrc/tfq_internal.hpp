@@ -129,6 +129,7 @@ struct Plan {
     Control *h_ctl = nullptr;         // pinned ring for control read-backs
     cudaEvent_t ev[8] = {nullptr};
     bool v3_ready = false, solved = false;
+    bool xop_of_x = false;            // the tensor-core operand currently holds v1 (made by setMatrix('X'); a solve overwrites it)
     bool configured = false;          // bufferSize succeeded: tiles, units and workspace offsets match LM, LN, precision
     // one tfQMR iteration body (8 iteration kernels + 3 probe kernels) as an instantiated CUDA graph; rebuilt when the
     // workspace or the block configuration changes
@@ -196,6 +197,7 @@ inline double* exchange_slots(Plan const &p, int kind) { return p.exch.slots + s
 tfqmrgpuStatus_t launch_decide(Plan const &p, int kind, cudaStream_t stream);
 // OP_K1 / OP_K3 that also emit the X operand of the fp16-pair tensor-core product from the v6 they write
 tfqmrgpuStatus_t launch_vecop_xop(Plan const &p, int op, cudaStream_t stream);
+tfqmrgpuStatus_t launch_unit_rhs(Plan const &p, cudaStream_t stream);   // B := unit blocks (the reference's rhs_trivial right-hand sides)
 // v[bpos[b]] += scal * B[b]   (linalg.hxx:383-428)
 tfqmrgpuStatus_t launch_add_rhs(Plan const &p, void *v, double scal, int expect, cudaStream_t stream);
 // host layout <-> internal layout (layout.cu)

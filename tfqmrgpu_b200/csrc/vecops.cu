@@ -710,6 +710,17 @@ vec_xop_kernel(VecArgs<float> const a)
     }
 }
 
+// B := unit blocks: b[Re][j % LM][j] = 1, everything else 0 (set_unit_blocks, linalg.hxx:432-455: the right-hand sides of the
+// reference's `rhs_trivial` mode, core.hxx:140-147, "columns of the unit matrix")
+template <typename real_t>
+__global__ void unit_blocks_kernel(real_t *__restrict__ B, int LM, int LN) {
+    size_t const base = size_t(blockIdx.x)*2*LM*LN;
+    for (int q = threadIdx.x; q < 2*LM*LN; q += blockDim.x) {
+        int const c = q/(LM*LN), i = (q/LN) % LM, j = q % LN;
+        B[base + q] = real_t((0 == c && i == j % LM) ? 1 : 0);
+    }
+}
+
 // v[bpos[b]] += scal*B[b]  (add_RHS, linalg.hxx:383-404)
 template <typename real_t>
 __global__ void add_rhs_kernel(real_t *__restrict__ v, real_t const *__restrict__ B, real_t scal,
@@ -826,6 +837,16 @@ tfqmrgpuStatus_t launch_vecop(Plan const &p, int op, cudaStream_t stream)
     } else {
         return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, p.precision);
     }
+    TFQ_CUDA(cudaGetLastError());
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
+tfqmrgpuStatus_t launch_unit_rhs(Plan const &p, cudaStream_t stream)
+{
+    if (p.nnzbB < 1) return TFQMRGPU_STATUS_SUCCESS;
+    int const threads = std::min(256, ((2*p.LM*p.LN + 31)/32)*32);
+    if ('z' == p.precision) unit_blocks_kernel<double><<<p.nnzbB, threads, 0, stream>>>(ws<double>(p, p.off_B), p.LM, p.LN);
+    else                    unit_blocks_kernel<float ><<<p.nnzbB, threads, 0, stream>>>(ws<float >(p, p.off_B), p.LM, p.LN);
     TFQ_CUDA(cudaGetLastError());
     return TFQMRGPU_STATUS_SUCCESS;
 }
