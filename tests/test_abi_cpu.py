@@ -132,6 +132,34 @@ def test_fortran_shims_without_gpu():
     lib.tfqmrgpuprinterror_(C.byref(code), C.byref(stat)); assert stat.value == 0
 
 
+def test_fortran_module_binds_the_exported_shims_with_their_argument_counts():
+    """include/tfqmrgpu_Fortran_module.F90 cannot be compiled in this image (no Fortran compiler): check statically that every
+    bind(C) interface names one of the 18 exported shims and passes as many arguments as the C shim takes
+    (tfqmrgpu_Fortran_wrappers.c:58-187), and that all 18 are bound."""
+    f90 = open(os.path.join(ROOT, "include", "tfqmrgpu_Fortran_module.F90")).read()
+    f90 = re.sub(r"&\s*\n\s*&?", " ", f90)                                   # join continuation lines
+    f90 = "\n".join(line.split("!")[0] for line in f90.splitlines())           # strip comments
+    binds = re.findall(r"subroutine\s+\w+\s*\(([^)]*)\)\s*bind\s*\(\s*C\s*,\s*name\s*=\s*\"(\w+)\"\s*\)", f90, flags=re.I)
+    assert binds
+    csrc = open(os.path.join(ROOT, "tfqmrgpu_b200", "csrc", "fortran_wrappers.c")).read()
+    csrc = re.sub(r"/\*.*?\*/", "", csrc, flags=re.S)
+    cargs = {name: len([a for a in args.split(",") if a.strip()])
+             for name, args in re.findall(r"^void\s+(\w+_)\s*\(([^)]*)\)", csrc, flags=re.M | re.S)}
+    assert sorted(cargs) == sorted(L.FORTRAN_SYMBOLS) and len(cargs) == 18
+    bound = {}
+    for args, name in binds:
+        assert name in cargs, name
+        bound[name] = len([a for a in args.split(",") if a.strip()])
+    assert sorted(bound) == sorted(cargs)
+    for name, n in bound.items():
+        assert n == cargs[name], (name, n, cargs[name])
+    # the constants of the fixed-form header are those of tfqmrgpu.h
+    hdr = open(os.path.join(ROOT, "include", "tfqmrgpu_Fortran.h")).read()
+    for name, value in (("TFQMRGPU_STATUS_SUCCESS", 0), ("TFQMRGPU_LAYOUT_RRRRIIII", 15), ("TFQMRGPU_LAYOUT_RIRIRIRI", 85)):
+        m = re.search(name + r"\s*=?\s*(\d+)", hdr)
+        assert m and int(m.group(1)) == value, name
+
+
 def test_python_package_refuses_to_run_without_library(tmp_path, monkeypatch):
     monkeypatch.setattr(L, "_lib", None)
     monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "missing.so"))
