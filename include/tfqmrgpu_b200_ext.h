@@ -114,11 +114,12 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getDevices(tfqmrgpuBsrsvPlan_t plan, int *nDevi
  *     in place and on `stream`, the nShards blocks of 4 doubles starting at the pointer it is given (block `shard` is this
  *     rank's contribution; NCCL: ncclAllGather(ptr + 4*shard, ptr, 4, ncclDouble, comm, stream)).  nRhsGlobal = number of
  *     right-hand sides over all shards.  hook == NULL removes the exchange.
- *     setShardHints (before bufferSize): X blocks per vector tile (tfqmrgpux_tileBlocksFor) and block columns per block row of
- *     the UNSHARDED problem - with them a shard tiles its vectors and chooses its product kernel like the single-GPU plan and
- *     reproduces the single-GPU bits of its columns when every block row of X holds the same block columns (a dense X, the
- *     reference's use case); for ragged X patterns the products group a row's entries by the block columns that share a
- *     unit, and results agree to rounding (same iteration count unless a decision falls within that rounding). */
+ *     setShardHints (before bufferSize): maxColsPerRowHint = block columns per block row of the UNSHARDED problem - with it a
+ *     shard chooses its product kernel like the single-GPU plan (the vector tiles are cut per block column, so they agree
+ *     anyway) and reproduces the single-GPU bits of its columns when every block row of X holds the same block columns (a
+ *     dense X, the reference's use case); for ragged X patterns the products group a row's entries by the block columns that
+ *     share a unit, and results agree to rounding (same iteration count unless a decision falls within that rounding).
+ *     tileBlocksHint > 0 forces a tile size (experiments); 0 = the default per-column rule (tfqmrgpux_tileBlocksFor). */
 typedef int32_t (*tfqmrgpuxExchange_t)(void *ctx, double *slots, int count, cudaStream_t stream);
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_setShardExchange(tfqmrgpuBsrsvPlan_t plan, int shard, int nShards, int64_t nRhsGlobal,
     double *slots, tfqmrgpuxExchange_t hook, void *ctx);
@@ -132,7 +133,7 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_setMatrixPart(tfqmrgpuHandle_t handle, tfqmrgpu
     char transposition, tfqmrgpuDataLayout_t layout, int part, int nParts, int64_t info[6]);
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_setShardHints(tfqmrgpuBsrsvPlan_t plan, int64_t tileBlocksHint, int32_t maxColsPerRowHint);
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_getTileBlocks(tfqmrgpuBsrsvPlan_t plan, int64_t *tileBlocks);
-/* what bufferSize would choose for a plan with nnzbX X blocks of blockBytes on the current device (the hint for the shards) */
+/* X blocks per vector tile that bufferSize chooses for a block column of nnzbX blocks of blockBytes on the current device */
 tfqmrgpuStatus_t tfqmrgpux_tileBlocksFor(int64_t nnzbX, int64_t blockBytes, int64_t *tileBlocks);
 
 #ifdef __cplusplus

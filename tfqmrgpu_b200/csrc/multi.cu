@@ -205,7 +205,6 @@ tfqmrgpuStatus_t multi_buffer_size(Plan &p, int LM, int LN, char prec, size_t *b
     p.vecBytes = size_t(p.nnzbX)*blockBytes;
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, m.home);
-    size_t const tile_blocks = plan_tile_blocks(size_t(p.nnzbX), blockBytes, nsm);   // what the unsharded plan would choose
     int const n = int(m.shards.size());
     for (int s = 0; s < n; ++s) {
         Shard &sh = m.shards[s];
@@ -214,7 +213,7 @@ tfqmrgpuStatus_t multi_buffer_size(Plan &p, int LM, int LN, char prec, size_t *b
         Plan &sp = *sh.plan;
         sp.pBuffer = nullptr; sp.bufferBytes = 0; sp.v3_ready = false; sp.configured = false;
         plan_drop_graph(sp);
-        sp.tile_blocks_hint = tile_blocks;
+        sp.tile_blocks_hint = p.tile_blocks_hint;   // (tiles are cut per column: a shard tiles its columns like the unsharded plan anyway)
         sp.max_cols_hint = p.maxColsPerRow;
         tfqmrgpuStatus_t const st = plan_configure(sp, sh.stream, LM, LN, prec);
         if (TFQMRGPU_STATUS_SUCCESS != st) return st;

@@ -382,15 +382,20 @@ void plan_release(Plan &p) {
     for (auto &e : p.chunk_ev) if (e) cudaEventDestroy(e);
 }
 
-// X blocks per vector tile: 16 KiB of a vector per tile, 4 KiB when that would leave SMs without a tile (FD_problem.xml, 175 KB
-// per vector: 2.98 -> 2.64 ms per solve; on the 1728-row sweep 16 KiB is the better one); at least nnzbX / (4 tiles per SM)
-size_t plan_tile_blocks(size_t nnzbX, size_t blockBytes, int nsm)
+// X blocks per vector tile of a block column with nColBlocks blocks.  The rule looks at the COLUMN only (its length, the block
+// size, the SM count), never at how many columns the plan has: a column is then cut into the same tiles - and its sums are added in
+// the same order - whether it is solved alone, with all other columns, or in a shard of them on another GPU.  (A first version
+// sized the tiles by the whole plan and shards had to be told the unsharded plan's tile size: an 8-GPU shard then ran its
+// vector kernels on 1/8 of the CTAs, 75 instead of 50 ms per solve at config 3.)
+// At least 16 KiB of a vector per tile, 4 KiB when the column is so short that this would leave most SMs without a tile
+// (FD_problem.xml, 25 KB per column: 2.98 -> 2.64 ms per solve); long columns: 2 tiles per SM and column.
+size_t plan_tile_blocks(size_t nColBlocks, size_t blockBytes, int nsm)
 {
-    size_t const target = size_t(nsm)*4;
-    size_t tb = std::max<size_t>(1, (nnzbX + target - 1)/target);
+    size_t const target = size_t(nsm)*2;
+    size_t const tb = std::max<size_t>(1, (nColBlocks + target - 1)/target);
     char const *env_tile = std::getenv("TFQMRGPU_TILE_KB");      // dev switch: minimum bytes of one vector per tile
-    size_t const vec_bytes = nnzbX*blockBytes;
-    size_t const tile_kb = env_tile ? size_t(std::max(1, std::atoi(env_tile))) : ((vec_bytes/(16*1024) < size_t(nsm)) ? 4 : 16);
+    size_t const col_bytes = nColBlocks*blockBytes;
+    size_t const tile_kb = env_tile ? size_t(std::max(1, std::atoi(env_tile))) : ((col_bytes/(16*1024) < size_t(nsm)) ? 4 : 16);
     size_t const tb_min = std::max<size_t>(1, (tile_kb*1024 + blockBytes - 1)/blockBytes);
     return std::max(tb, tb_min);
 }
@@ -411,14 +416,14 @@ tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, ch
 
     // ---- vector tiles: every tile is a contiguous range of blocks of ONE block column ---------------
     {
-        size_t tb = plan_tile_blocks(size_t(p.nnzbX), blockBytes, nsm);
-        if (p.tile_blocks_hint > 0) tb = p.tile_blocks_hint;          // a shard tiles its columns like the unsharded plan does
-        p.tile_blocks = tb;
+        p.tile_blocks = 0;
         std::vector<Tile> tiles;
         std::vector<uint32_t> coltile(size_t(nb) + 1, 0);
         for (uint32_t c = 0; c < nb; ++c) {
             uint32_t const b0 = p.h_colstart[c], b1 = p.h_colstart[c + 1];
             uint32_t const n = b1 - b0;
+            size_t const tb = (p.tile_blocks_hint > 0) ? p.tile_blocks_hint : plan_tile_blocks(n, blockBytes, nsm);
+            p.tile_blocks = std::max(p.tile_blocks, tb);
             uint32_t const nt = std::max<uint32_t>(1, uint32_t((n + tb - 1)/tb));
             coltile[c] = uint32_t(tiles.size());
             for (uint32_t t = 0; t < nt; ++t) {

@@ -95,9 +95,9 @@ struct Plan {
     bool use_dmma = false;            // complex fp64 product on the FP64 tensor pipe (spmm_dmma.cu)
     Exchange exch;
     struct MultiPlan *multi = nullptr;       // in-process multi-GPU plan (multi.cu): this Plan is then only the global analysis
-    size_t tile_blocks = 0;                  // X blocks per vector tile chosen by plan_configure
+    size_t tile_blocks = 0;                  // X blocks per vector tile chosen by plan_configure (largest over the block columns)
     int    max_cols_hint = 0;               // ... and choose the product kernel by the unsharded plan's block columns per row
-    size_t tile_blocks_hint = 0;             // shards tile their vectors like the unsharded plan (same reduction order, same bits)
+    size_t tile_blocks_hint = 0;             // > 0: forced tile size (dev / experiments); the default rule is per block column
     tfqmrgpuxOperator_t user_op = nullptr;   // user-defined operator instead of the block-sparse product (ext header)
     void *user_ctx = nullptr;
     bool use_small = false;           // LM <= 8: register-staged batches of entries instead of the bulk-copy ring (spmm.cu)
@@ -155,7 +155,7 @@ tfqmrgpuStatus_t plan_analyse(Plan &p, cudaStream_t stream,
 tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, char precision); // tiles, units, offsets
 void plan_release(Plan &p);
 void plan_drop_graph(Plan &p);   // forget the captured iteration body
-size_t plan_tile_blocks(size_t nnzbX, size_t blockBytes, int nsm);   // X blocks per vector tile that plan_configure chooses
+size_t plan_tile_blocks(size_t nColBlocks, size_t blockBytes, int nsm);   // X blocks per vector tile for a block column of that length
 
 // ---- several devices in one process (multi.cu) ---------------------------------------------------------
 tfqmrgpuStatus_t multi_set_devices(Plan &p, int nDevices, int const *devices);

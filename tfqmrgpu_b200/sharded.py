@@ -11,7 +11,7 @@ Convergence control: the reference's iteration counter and probe schedule are GL
 all right-hand sides decides (core.hxx:239-299).  With a process group (``dist``) every rank registers an
 exchange (``tfqmrgpux_bsrsv_setShardExchange``): after K4 and after N3 the ranks all-gather three numbers
 per shard on the solver's stream (NCCL) and take the same decision, so an N-rank run has the single-GPU
-iteration count and - the shards tile their vectors like the unsharded plan - the single-GPU bits.
+iteration count and - vector tiles are cut per block column, whatever the shard - the single-GPU bits.
 Without a process group (ranks solved one after the other, e.g. on one GPU) every shard runs the rule on
 its own columns and may stop earlier than the global maximum would.
 
@@ -96,9 +96,12 @@ class NcclExchange:
         self.slots = torch.zeros(2*2*world*4, dtype=torch.float64, device=device)
         self.mine = torch.zeros(4, dtype=torch.float64, device=device)
         self.calls = 0
+        self.cpu_s = 0.0                  # host time spent in the hook (diagnostics)
         base = self.slots.data_ptr()
 
         def hook(ptr, count, stream):
+            import time
+            t0 = time.perf_counter()
             off = (ptr - base)//8
             view = self.slots[off:off + count]
             ext = torch.cuda.ExternalStream(stream, device=device) if stream else torch.cuda.default_stream(device)
@@ -106,6 +109,7 @@ class NcclExchange:
                 self.mine.copy_(view[4*rank:4*rank + 4])
                 dist.all_gather_into_tensor(view, self.mine)
             self.calls += 1
+            self.cpu_s += time.perf_counter() - t0
             return 0
         plan.set_shard_exchange(rank, world, n_rhs_global, base, hook)
 
@@ -133,9 +137,9 @@ class ShardedBsrsv:
         ciA0 = np.asarray(ciA, np.int32) - index_offset
         self.plan = api.BsrsvPlan(self.handle, mb, rpA0, ciA0, s.rpX, s.ciX, s.rpB, s.ciB, 0, 0)
         if world > 1:
-            # tile the shard's vectors like the unsharded plan would (same reduction order -> same bits)
+            # choose the product kernel like the unsharded plan would (vector tiles are cut per block column: they agree anyway)
             max_cols = int(np.diff(np.asarray(rpX, np.int64)).max())
-            self.plan.set_shard_hints(api.tile_blocks_for(s.nnzbX_global, 2*lm*ln*(8 if precision == "z" else 4)), max_cols)
+            self.plan.set_shard_hints(0, max_cols)
         if dist is not None and world > 1:
             self._register_exchange(dist, rank, world, s.ncols_global*ln)
         nbytes = self.plan.buffer_size_for(lm, ln, precision)
