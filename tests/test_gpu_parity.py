@@ -797,3 +797,84 @@ def test_rhs_trivial_equals_uploaded_unit_blocks(lm, ln, prec, tol):
         pl.close(); h.close()
     assert out[0][0] == out[1][0] == 0 and out[0][1] == out[1][1] and np.array_equal(out[0][2], out[1][2])
 
+
+
+def _one_block_per_row_system(mb, lm, ln, nc, seed):
+    """A of random_system, X with ONE block per block row (row r holds block column r % nc, like the truncated solutions of the
+    reference's FD example), B = one block per column."""
+    base = P.random_system(mb, lm, ln, ncols=nc, seed=seed, unsorted=True)
+    rng = np.random.default_rng(seed + 1)
+    rpX = np.arange(mb + 1, dtype=np.int32); ciX = (np.arange(mb) % nc).astype(np.int32)
+    counts = np.zeros(mb, np.int64); counts[:nc] = 1
+    rpB = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32); ciB = np.arange(nc, dtype=np.int32)
+    valB = rng.uniform(-.5, .5, (nc, lm, ln)) + 1j*rng.uniform(-.5, .5, (nc, lm, ln))
+    return P.Problem(base.A, P.Bsr(rpX, ciX, None), P.Bsr(rpB, ciB, valB), lm, ln, 1e-6, f"one_per_row_{lm}x{ln}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["fd", (4, 4, "c", 1), (8, 8, "c", 3), (8, 32, "c", 2), (4, 5, "c", 2), (8, 10, "z", 2), (4, 8, "z", 3),
+                                   (8, 8, "z", 1), (8, 64, "z", 2)], ids=str)
+def test_resident_solver_matches_the_per_kernel_path(which, golden, monkeypatch):
+    """Small systems with one X block per block row are solved in ONE cooperative launch (resident.cu: every CTA owns a vector
+    tile in shared memory).  Same status and iteration count (+-1) as the per-kernel path (TFQMRGPU_RESIDENT=0), X equal to
+    rounding and to the oracle's, the true residual below the tolerance, and the launch count says which path ran.  Two solves on
+    the same plan give the same bits (the barrier state is reset per solve)."""
+    if which == "fd":
+        prob = P.read_xml(os.path.join(HERE, "golden", "FD_problem.xml")); prec, tol, tA, tB = "z", prob.tolerance, "t", "t"
+    else:
+        lm, ln, prec, nc = which
+        prob = _one_block_per_row_system(60, lm, ln, nc, seed=lm*10 + ln)
+        tol, tA, tB = (1e-9 if prec == "z" else 1e-4), "n", "n"
+    dt = np.float64 if prec == "z" else np.float32
+    vA = P.interleave(prob.A.val, dt); vB = P.interleave(prob.B.val, dt)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("TFQMRGPU_RESIDENT", mode)
+        h, pl = _open(prob)
+        pl.buffer_size_for(prob.lm, prob.ln, prec); pl.set_buffer()
+        pl.set_matrix("A", vA, tA); pl.set_matrix("B", vB, tB)
+        st = pl.solve(tol, 500)
+        X = pl.get_matrix("X", "n", L.LAYOUT_RRRRIIII).copy()
+        info, stats, rhs = pl.info(), pl.solve_stats(), pl.rhs_status()
+        st2 = pl.solve(tol, 500)
+        X2 = pl.get_matrix("X", "n", L.LAYOUT_RRRRIIII)
+        assert st2 == st and np.array_equal(X, X2)
+        out[mode] = (st, info, stats, X.reshape(pl.nnzbX, 2, prob.lm, prob.ln), rhs)
+        pl.close(); h.close()
+    (s0, i0, t0, X0, r0), (s1, i1, t1, X1, r1) = out["0"], out["1"]
+    assert t1["launches"] == 3 and t0["launches"] > 3                  # begin (2) + the one cooperative launch
+    assert s0 == s1 == 0
+    assert abs(i0["iterations"] - i1["iterations"]) <= 1
+    assert i1["residuum"] <= tol
+    assert np.array_equal(r0, r1)
+    if i0["iterations"] == i1["iterations"] and t0["probes"] == t1["probes"]:
+        assert i0["flops"] == i1["flops"]
+    assert np.abs(X1 - X0).max() <= (10 if prec == "z" else 50)*tol*np.abs(X0).max()
+    assert _true_residual(prob, X1.astype(np.float64), tA, tB) <= (tol*1.01 if prec == "z" else 5*tol)
+
+
+@pytest.mark.gpu
+def test_resident_solver_max_iterations_and_breakdown(monkeypatch):
+    """status 9 with iterations_needed == MaxIt from the resident loop; a zero shadow vector breaks down and a zero right-hand side
+    stops after one iteration exactly like on the per-kernel path (same status, iterations and per-right-hand-side status)."""
+    prob = _one_block_per_row_system(30, 8, 8, 2, seed=5)
+    vA = P.interleave(prob.A.val, np.float64); vB = P.interleave(prob.B.val, np.float64)
+    h, pl = _open(prob)
+    pl.buffer_size_for(8, 8, "z"); pl.set_buffer()
+    pl.set_matrix("A", vA); pl.set_matrix("B", vB)
+    assert pl.solve(1e-9, 3) == L.STATUS_MAX_ITERATIONS
+    assert pl.info()["iterations"] == 3 and pl.solve_stats()["launches"] == 3
+    assert pl.solve(1e-9, 200) == 0 and pl.solve_stats()["launches"] == 3
+    v3 = pl.get_v3().copy()
+    for zero_v3, b in ((True, vB), (False, 0*vB)):
+        pl.set_v3(0*v3 if zero_v3 else v3)
+        pl.set_matrix("B", b)
+        res = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("TFQMRGPU_RESIDENT", mode)
+            st = pl.solve(1e-9, 50)
+            res[mode] = (st, pl.info()["iterations"], pl.rhs_status().copy(), pl.solve_stats()["launches"])
+        assert res["0"][0] == res["1"][0] == (L.STATUS_BREAKDOWN if zero_v3 else 0)
+        assert res["0"][1] == res["1"][1] and np.array_equal(res["0"][2], res["1"][2])
+        assert res["1"][3] == 3 and res["0"][3] > 3
+    pl.close(); h.close()

@@ -367,6 +367,7 @@ static void free_configured(Plan &p) {
     cudaFree(p.d_ent_x); p.d_ent_x = nullptr;
     cudaFree(p.d_cta_u0); p.d_cta_u0 = nullptr;
     cudaFree(p.d_unit_row); p.d_unit_row = nullptr;
+    cudaFree(p.d_unit_of_block); p.d_unit_of_block = nullptr;
 }
 
 void plan_release(Plan &p) {
@@ -374,6 +375,8 @@ void plan_release(Plan &p) {
     free_configured(p);
     cudaFree(p.d_starts); cudaFree(p.d_pairs); cudaFree(p.d_subset); cudaFree(p.d_colindx);
     cudaFree(p.d_perm); cudaFree(p.d_iperm); cudaFree(p.d_bpos); cudaFree(p.d_blockcol); cudaFree(p.d_rowptrA);
+    if (p.d_resident_bar) cudaFree(p.d_resident_bar);
+    if (p.d_resident_trace) cudaFree(p.d_resident_trace);
     if (p.h_ctl) cudaFreeHost(p.h_ctl);
     for (auto &e : p.ev) if (e) cudaEventDestroy(e);
     for (auto &e : p.prof_ev) if (e) cudaEventDestroy(e);

@@ -217,7 +217,8 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
     auto mark = [&](int which) { return p.profile ? cudaEventRecord(p.prof_ev[which], stream) : cudaSuccess; };
     TFQ_CUDA(mark(0));
     // (a callback cannot be captured blindly; the exchange hook of a sharded run is a host call per iteration)
-    bool const use_graph = graphs_enabled() && !p.profile && maxIterations > 0 && nullptr == p.user_op && nullptr == p.exch.slots;
+    bool const use_graph = graphs_enabled() && !p.profile && maxIterations > 0 && nullptr == p.user_op && nullptr == p.exch.slots
+                           && !resident_supported(p);
     if (use_graph && nullptr == p.body_exec) {
         tfqmrgpuStatus_t const gst = build_body_graph(p);
         if (TFQMRGPU_STATUS_SUCCESS != gst) return gst;
@@ -235,7 +236,14 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
     TfqRange const range_iter("tfQMR iterations");
 
     int bodies = 0;
-    for (int i = 0; i < maxIterations; ++i) {
+    // small systems: the whole solve in one cooperative launch (resident.cu); the loop below is skipped
+    bool const resident = maxIterations > 0 && resident_supported(p);
+    if (resident) {
+        st = launch_resident_solve(p, stream, maxIterations);
+        if (TFQMRGPU_STATUS_SUCCESS != st) return st;
+        launches += 1;
+    }
+    for (int i = 0; i < maxIterations && !resident; ++i) {
         if (i >= kAhead) {
             int const slot = (i - kAhead) % kRing;
             TFQ_CUDA(cudaEventSynchronize(p.ev[slot]));
@@ -273,6 +281,7 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
             }
         }
     }
+    if (resident) bodies = fin.iteration;
     tfqmrgpuStatus_t const result = solve_finish(p, fin, bodies, launches);
     p.stat_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
     if (verbosity() > 1)

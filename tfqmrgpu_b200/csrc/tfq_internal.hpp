@@ -95,6 +95,9 @@ struct Plan {
     bool use_dmma = false;            // complex fp64 product on the FP64 tensor pipe (spmm_dmma.cu)
     Exchange exch;
     struct MultiPlan *multi = nullptr;       // in-process multi-GPU plan (multi.cu): this Plan is then only the global analysis
+    unsigned *d_resident_bar = nullptr;      // grid barrier of the resident solver (resident.cu)
+    unsigned long long *d_resident_trace = nullptr;   // dev: time breakdown of the resident solver (TFQMRGPU_RESIDENT_TRACE)
+    uint32_t *d_unit_of_block = nullptr;     // resident solver: storage index of a Y block -> its unit (plans with gmax == 1)
     size_t tile_blocks = 0;                  // X blocks per vector tile chosen by plan_configure (largest over the block columns)
     int    max_cols_hint = 0;               // ... and choose the product kernel by the unsharded plan's block columns per row
     size_t tile_blocks_hint = 0;             // > 0: forced tile size (dev / experiments); the default rule is per block column
@@ -155,6 +158,9 @@ tfqmrgpuStatus_t plan_analyse(Plan &p, cudaStream_t stream,
 tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, char precision); // tiles, units, offsets
 void plan_release(Plan &p);
 void plan_drop_graph(Plan &p);   // forget the captured iteration body
+// the resident solver (resident.cu): a whole solve of a small system in one cooperative launch
+bool resident_supported(Plan &p);
+tfqmrgpuStatus_t launch_resident_solve(Plan &p, cudaStream_t stream, int maxIterations);
 size_t plan_tile_blocks(size_t nColBlocks, size_t blockBytes, int nsm);   // X blocks per vector tile for a block column of that length
 
 // ---- several devices in one process (multi.cu) ---------------------------------------------------------
