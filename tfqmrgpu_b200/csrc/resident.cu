@@ -24,6 +24,8 @@
 // also compiled with -Xptxas -dlcm=cg, so a plain load that slipped in would still be correct.
 #include "vec_body.cuh"
 #include <cstdlib>
+#include <cstdio>
+#include <vector>
 
 namespace tfq {
 
@@ -50,8 +52,10 @@ template <typename real_t> struct ResidentArgs {
     uint32_t tile_blocks;                     // blocks of the largest tile
     int eb;                                   // entries staged per batch and warp
     int max_e;                                // entries per Y block whose indices (and, a_resident, A blocks) are kept in shared memory
+    int warps_per_block;                      // warps that share one Y block in the product (1, 2 or 4)
     int a_resident;                           // the A blocks of the tile's rows stay in shared memory for the whole solve
-    unsigned long long *trace;                // dev: time of CTA 0 in [barriers, products, column sums, total] (ns), or nullptr
+    int ablate;                               // dev: 1 = skip the FMAs of the product, 2 = skip its global loads
+    unsigned long long *trace;                // dev: cycles of CTA 0 in [barriers, products, column sums, total, ...], or nullptr
 };
 
 __device__ __forceinline__ unsigned long long res_now_ns() {
@@ -98,6 +102,7 @@ resident_solve_kernel(ResidentArgs<real_t> const a)
     constexpr int BA = 2*LM*LM;                // reals per A block
     constexpr int R = kResThreads/LN;          // thread rows per lane j
     constexpr int TJ = res_tj(LM, LN);
+    constexpr int KS = (TJ <= 2) ? 4 : ((TJ <= 4) ? 2 : 1);       // accumulator sets in the product (see there)
     constexpr int aF4 = int(BA*sizeof(real_t)/16), xF4 = int(BE*sizeof(real_t)/16);
     static_assert((BA*sizeof(real_t)) % 16 == 0 && (BE*sizeof(real_t)) % 16 == 0, "blocks are whole float4s");
     static_assert(LN <= 64 && R >= 1 && 2*LN <= kResThreads, "lane count");
@@ -130,7 +135,8 @@ resident_solve_kernel(ResidentArgs<real_t> const a)
     uint32_t *const s_ea = s_e0 + 2*a.tile_blocks;                                  // [tile_blocks][max_e] A block of an entry
     uint32_t *const s_ex = s_ea + size_t(a.tile_blocks)*a.max_e;                      // [tile_blocks][max_e] X block (storage index)
     real_t *const s_A = reinterpret_cast<real_t*>((reinterpret_cast<uintptr_t>(s_ex + size_t(a.tile_blocks)*a.max_e) + 15) & ~uintptr_t(15));
-    float4 *const s_stage = reinterpret_cast<float4*>(s_A + (a.a_resident ? size_t(a.tile_blocks)*a.max_e*BA : 0));
+    real_t *const s_yp = s_A + (a.a_resident ? size_t(a.tile_blocks)*a.max_e*BA : 0);             // [kResWarps][BE] partial Y blocks
+    float4 *const s_stage = reinterpret_cast<float4*>(s_yp + size_t(kResWarps)*BE);
 
     // the recurrences of vec_body.cuh work on this CTA's copy of its column's scalars (column index 0)
     VecArgs<real_t> sv;
@@ -176,6 +182,8 @@ resident_solve_kernel(ResidentArgs<real_t> const a)
     bool const act = rt < R;
     unsigned redphase = 0;                     // partial sums are double-buffered by the parity of the reduction
     unsigned passed = 0;                       // grid barriers passed so far
+    bool const tracing = (nullptr != a.trace) && 0 == blockIdx.x && 0 == tid;     // dev: cycle counts of CTA 0, thread 0, kept in registers
+    long long tr_bar = 0, tr_prod = 0, tr_sum = 0, tr_stage = 0, tr_fma = 0;
     long long const nRHS = (long long)(a.nCols)*LN;
 
     // element (row q of the tile, lane j): Re at idx, Im at idx + PL
@@ -185,7 +193,7 @@ resident_solve_kernel(ResidentArgs<real_t> const a)
     // added by kResThreads / (D*LN) slices of threads (slice s takes the tiles t0 + s, t0 + s + S, ...: independent loads in
     // flight instead of one dependent chain), then the slices in order: the same grouping in every CTA of the column.
     auto reduce = [&](double acc0, double acc1, int D) {
-        unsigned long long const tr0 = (a.trace && 0 == blockIdx.x && 0 == tid) ? res_now_ns() : 0;
+        long long const tr0 = tracing ? clock64() : 0;
         if (act) { s_red[(rt*2 + 0)*LN + j] = acc0; s_red[(rt*2 + 1)*LN + j] = acc1; }
         __syncthreads();
         unsigned const par = (redphase++) & 1u;
@@ -195,9 +203,9 @@ resident_solve_kernel(ResidentArgs<real_t> const a)
             for (int r = 0; r < R; ++r) s += s_red[(r*2 + d)*LN + jj];
             a.part[(size_t(blockIdx.x)*kPartD + par*2 + d)*LN + jj] = s;
         }
-        unsigned long long const tb0 = tr0 ? res_now_ns() : 0;
+        long long const tb0 = tracing ? clock64() : 0;
         grid_barrier(a.bar, nCta, passed);
-        if (tr0) a.trace[0] += res_now_ns() - tb0;
+        if (tracing) tr_bar += clock64() - tb0;
         int const nq = D*LN, S = kResThreads/nq;
         int const q = tid % nq, sl = tid / nq;
         if (sl < S) {
@@ -214,7 +222,7 @@ resident_solve_kernel(ResidentArgs<real_t> const a)
             s_sum[tid] = s;                      // [d*LN + j]
         }
         __syncthreads();
-        if (tr0) a.trace[2] += res_now_ns() - tr0;
+        if (tracing) tr_sum += clock64() - tr0;
     };
 
     // the tile's v6 (or v1) to global memory for the other tiles' products
@@ -223,84 +231,127 @@ resident_solve_kernel(ResidentArgs<real_t> const a)
         for (int q = tid; q < nb*BE; q += kResThreads) dst[q] = s[q];
     };
 
-    // Y blocks of this tile: y := A * x  (blocksparse.hxx:71-199, blockmult.hxx:28-82: all entries and k in order, one accumulator).
+    // Y blocks of this tile: y := A * x  (blocksparse.hxx:71-199, blockmult.hxx:28-82).
     // One warp per Y block.  The entry indices are in shared memory (s_ea / s_ex, loaded once), the A blocks too when they fit
     // (a_resident: A is read from global memory ONCE per solve), and the X blocks of a batch of entries are fetched with all
     // their 128-bit loads in flight before the first one is stored to the staging area.
     auto product = [&](real_t *sy, real_t const *gx) {
-        unsigned long long const tp0 = (a.trace && 0 == blockIdx.x && 0 == tid) ? res_now_ns() : 0;
+        long long const tp0 = tracing ? clock64() : 0;
         int const i = lane % LM, jg = lane / LM;
         bool const on = jg < LN/TJ;
         int const perE = a.a_resident ? xF4 : (aF4 + xF4);         // float4s staged per entry
         float4 *const st4 = s_stage + size_t(warp)*a.eb*perE;
         float4 const *const A4 = reinterpret_cast<float4 const*>(a.A);
         float4 const *const X4 = reinterpret_cast<float4 const*>(gx);
-        for (int yb = warp; yb < nb; yb += kResWarps) {
-            uint32_t const e0 = s_e0[yb], e1 = s_e0[a.tile_blocks + yb];
-            real_t acr[TJ], aci[TJ];
-            #pragma unroll
-            for (int jj = 0; jj < TJ; ++jj) { acr[jj] = 0; aci[jj] = 0; }
-            for (uint32_t eb0 = e0; eb0 < e1; eb0 += a.eb) {
-                int const ne = int(min(uint32_t(a.eb), e1 - eb0));
-                int const total = ne*perE;
-                __syncwarp();
-                for (int base = 0; base < total; base += 32*kResLoads) {
-                    float4 reg[kResLoads];
+        // W warps share a Y block: warp `ws` of the group takes the block's entries ws, ws + W, ... and the partial sums are
+        // added in the order of the warps (a fixed grouping: W follows from the tile size alone)
+        int const W = a.warps_per_block, groups = kResWarps/W;
+        int const grp = warp / W, ws = warp - grp*W;
+        for (int yb0 = 0; yb0 < nb; yb0 += groups) {
+            int const yb = yb0 + grp;
+            if (yb < nb) {
+                uint32_t const e0 = s_e0[yb], e1 = s_e0[a.tile_blocks + yb];
+                int const mine = (int(e1 - e0) > ws) ? (int(e1 - e0) - ws + W - 1)/W : 0;     // entries of this warp
+                // KS independent accumulators per output (k = ks mod KS): one warp per scheduler cannot hide the latency of a
+                // chain of dependent fp64 FMAs (measured ~40 cycles each), so the chains are made short and many
+                real_t acr[KS][TJ], aci[KS][TJ];
+                #pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
                     #pragma unroll
-                    for (int v = 0; v < kResLoads; ++v) {
-                        int const q = base + v*32 + lane;
-                        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (q < total) {
-                            int const e = q/perE, r = q - e*perE;
-                            int const le = int(eb0 - e0) + e;                   // entry number within the Y block
-                            if (r < perE - xF4) {
-                                uint32_t const ia = (le < a.max_e) ? s_ea[yb*a.max_e + le] : a.ent_a[eb0 + e];
-                                val = __ldg(A4 + size_t(ia)*aF4 + r);
-                            } else {
-                                uint32_t const ix = (le < a.max_e) ? s_ex[yb*a.max_e + le] : a.ent_x[eb0 + e];
-                                if (kNoBlock != ix) val = __ldcg(X4 + size_t(ix)*xF4 + (r - (perE - xF4)));
+                    for (int jj = 0; jj < TJ; ++jj) { acr[ks][jj] = 0; aci[ks][jj] = 0; }
+                }
+                for (int m0 = 0; m0 < mine; m0 += a.eb) {
+                    int const ne = min(a.eb, mine - m0);
+                    long long const tl0 = tracing ? clock64() : 0;
+                    __syncwarp();
+                    // per entry the block(s) are contiguous: lane l fetches float4 l, l + 32, ... of every block; all loads of a
+                    // chunk of entries are in flight before the first is stored (few instructions: one warp per scheduler pays
+                    // ~4 cycles for each)
+                    constexpr int LPE = (aF4 + xF4 + 31)/32;                  // loads per entry and lane (upper bound)
+                    constexpr int CHE = (kResLoads/LPE > 0) ? kResLoads/LPE : 1;   // entries per chunk
+                    for (int c0 = 0; c0 < ne; c0 += CHE) {
+                        float4 reg[CHE][LPE];
+                        #pragma unroll
+                        for (int ce = 0; ce < CHE; ++ce) {
+                            int const e = c0 + ce;
+                            int const le = ws + W*(m0 + e);                     // entry number within the Y block
+                            bool const live = (e < ne) && !(a.ablate & 2);
+                            uint32_t ia = 0, ix = kNoBlock;
+                            if (live) {
+                                if (!a.a_resident) ia = (le < a.max_e) ? s_ea[yb*a.max_e + le] : a.ent_a[e0 + le];
+                                ix = (le < a.max_e) ? s_ex[yb*a.max_e + le] : a.ent_x[e0 + le];
+                            }
+                            #pragma unroll
+                            for (int l = 0; l < LPE; ++l) {
+                                int const r = l*32 + lane;                      // float4 within the staged entry
+                                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (live && r < perE) {
+                                    if (r < perE - xF4) val = __ldg(A4 + size_t(ia)*aF4 + r);
+                                    else if (kNoBlock != ix) val = __ldcg(X4 + size_t(ix)*xF4 + (r - (perE - xF4)));
+                                }
+                                reg[ce][l] = val;
                             }
                         }
-                        reg[v] = val;
+                        #pragma unroll
+                        for (int ce = 0; ce < CHE; ++ce) {
+                            #pragma unroll
+                            for (int l = 0; l < LPE; ++l) {
+                                int const r = l*32 + lane;
+                                if (c0 + ce < ne && r < perE) st4[(c0 + ce)*perE + r] = reg[ce][l];
+                            }
+                        }
                     }
-                    #pragma unroll
-                    for (int v = 0; v < kResLoads; ++v) {
-                        int const q = base + v*32 + lane;
-                        if (q < total) st4[q] = reg[v];
+                    __syncwarp();
+                    if (tracing) tr_stage += clock64() - tl0;
+                    if (on && !(a.ablate & 1)) {
+                        for (int e = 0; e < ne; ++e) {
+                            int const le = ws + W*(m0 + e);
+                            real_t const *const Xs = reinterpret_cast<real_t const*>(st4 + size_t(e)*perE + (perE - xF4));
+                            real_t const *const As = a.a_resident ? (s_A + (size_t(yb)*a.max_e + le)*BA)
+                                                                  : reinterpret_cast<real_t const*>(st4 + size_t(e)*perE);
+                            #pragma unroll
+                            for (int k = 0; k < LM; ++k) {
+                                real_t const ar = As[k*LM + i], ai = As[LM*LM + k*LM + i];
+                                #pragma unroll
+                                for (int jj = 0; jj < TJ; ++jj) {
+                                    real_t const xr = Xs[k*LN + jg*TJ + jj], xi = Xs[PL + k*LN + jg*TJ + jj];
+                                    acr[k % KS][jj] = fma( ar, xr, acr[k % KS][jj]);         // complex multiply-accumulate (blockmult.hxx:76-77)
+                                    acr[k % KS][jj] = fma(-ai, xi, acr[k % KS][jj]);
+                                    aci[k % KS][jj] = fma( ar, xi, aci[k % KS][jj]);
+                                    aci[k % KS][jj] = fma( ai, xr, aci[k % KS][jj]);
+                                }
+                            }
+                        }
                     }
                 }
-                __syncwarp();
+                if (tracing) tr_fma += clock64() - tp0;
                 if (on) {
-                    for (int e = 0; e < ne; ++e) {
-                        int const le = int(eb0 - e0) + e;
-                        real_t const *const Xs = reinterpret_cast<real_t const*>(st4 + size_t(e)*perE + (perE - xF4));
-                        real_t const *const As = a.a_resident ? (s_A + (size_t(yb)*a.max_e + le)*BA)
-                                                              : reinterpret_cast<real_t const*>(st4 + size_t(e)*perE);
+                    real_t *const dst = (1 == W) ? (sy + yb*BE) : (s_yp + size_t(warp)*BE);
+                    #pragma unroll
+                    for (int jj = 0; jj < TJ; ++jj) {
+                        real_t sr = acr[0][jj], si = aci[0][jj];
                         #pragma unroll
-                        for (int k = 0; k < LM; ++k) {
-                            real_t const ar = As[k*LM + i], ai = As[LM*LM + k*LM + i];
-                            #pragma unroll
-                            for (int jj = 0; jj < TJ; ++jj) {
-                                real_t const xr = Xs[k*LN + jg*TJ + jj], xi = Xs[PL + k*LN + jg*TJ + jj];
-                                acr[jj] = fma( ar, xr, acr[jj]);         // complex multiply-accumulate (blockmult.hxx:76-77)
-                                acr[jj] = fma(-ai, xi, acr[jj]);
-                                aci[jj] = fma( ar, xi, aci[jj]);
-                                aci[jj] = fma( ai, xr, aci[jj]);
-                            }
-                        }
+                        for (int ks = 1; ks < KS; ++ks) { sr += acr[ks][jj]; si += aci[ks][jj]; }
+                        dst[i*LN + jg*TJ + jj] = sr;
+                        dst[PL + i*LN + jg*TJ + jj] = si;
                     }
                 }
             }
-            if (on) {
-                #pragma unroll
-                for (int jj = 0; jj < TJ; ++jj) {
-                    sy[yb*BE + i*LN + jg*TJ + jj] = acr[jj];
-                    sy[yb*BE + PL + i*LN + jg*TJ + jj] = aci[jj];
+            if (W > 1) {
+                __syncthreads();
+                for (int q = tid; q < groups*BE; q += kResThreads) {
+                    int const g = q / BE, el = q - g*BE;
+                    if (yb0 + g < nb) {
+                        real_t s = s_yp[size_t(g*W)*BE + el];
+                        for (int w2 = 1; w2 < W; ++w2) s += s_yp[size_t(g*W + w2)*BE + el];
+                        sy[(yb0 + g)*BE + el] = s;
+                    }
                 }
+                __syncthreads();
             }
         }
         __syncthreads();
-        if (tp0) a.trace[1] += res_now_ns() - tp0;
+        if (tracing) tr_prod += clock64() - tp0;
     };
 
     // the columns' monitors -> (max, sum, sum) over all columns, identical in every CTA
@@ -314,7 +365,7 @@ resident_solve_kernel(ResidentArgs<real_t> const a)
         }
     };
 
-    unsigned long long const tt0 = (a.trace && 0 == blockIdx.x && 0 == tid) ? res_now_ns() : 0;
+    long long const tt0 = tracing ? clock64() : 0;
     while (true) {
         int st = lc->state;                    // replicated: every CTA takes the same decisions from the same numbers
         if (STATE_DONE == st) break;
@@ -487,7 +538,10 @@ resident_solve_kernel(ResidentArgs<real_t> const a)
         }
     }
 
-    if (tt0) a.trace[3] = res_now_ns() - tt0;
+    if (tracing) {
+        a.trace[0] = tr_bar; a.trace[1] = tr_prod; a.trace[2] = tr_sum; a.trace[3] = clock64() - tt0; a.trace[4] = tr_stage; a.trace[5] = tr_fma;
+        a.trace[6] = (unsigned long long)(lc->iteration); a.trace[7] = (unsigned long long)(lc->probes);
+    }
     // ---- results: X, the per-right-hand-side status, the control block ---------------------------------------------------
     publish(a.v1, s_v1);
     if (first && tid < LN) { a.status[size_t(c)*LN + tid] = s_status[tid]; a.snap[size_t(c)*LN + tid] = s_snap[tid]; }
@@ -509,8 +563,43 @@ size_t resident_smem(size_t tile_blocks, int max_e, bool a_res, int eb) {
     b += (3*LN + 2*R*LN + 4*LN)*sizeof(double) + 10*LN*sizeof(real_t) + 2*LN + 16 + sizeof(Control);
     b += (2*tile_blocks + 2*tile_blocks*max_e)*sizeof(uint32_t) + 16;
     if (a_res) b += tile_blocks*max_e*2*LM*LM*sizeof(real_t);
+    b += size_t(kResWarps)*2*LM*LN*sizeof(real_t);
     b += size_t(kResWarps)*eb*((a_res ? 0 : 2*LM*LM) + 2*LM*LN)*sizeof(real_t);
     return b + 128;
+}
+
+// The resident solver cuts the vectors into its OWN tiles (not the plan's streaming tiles): one CTA per tile, so about one tile
+// per SM (TFQMRGPU_RESIDENT_TILES_PER_SM of them), each a range of blocks of one block column; tiles of 1 / 2 blocks put 4 / 2
+// warps on every Y block of the product.
+struct ResidentTiling { std::vector<Tile> tiles; std::vector<uint32_t> coltile; uint32_t tile_blocks = 0; };
+ResidentTiling resident_tiling(Plan const &p, int nsm) {
+    ResidentTiling rt;
+    char const *const e = std::getenv("TFQMRGPU_RESIDENT_TILES_PER_SM");
+    int const per_sm = e ? std::max(1, std::atoi(e)) : 1;
+    size_t const target = size_t(nsm)*per_sm;
+    // the smallest tile size that needs at most `target` tiles
+    uint32_t tb = std::max<uint32_t>(1, uint32_t((size_t(p.nnzbX) + target - 1)/target));
+    for (;; ++tb) {
+        size_t n = 0;
+        for (uint32_t c = 0; c < p.nCols; ++c) n += std::max<size_t>(1, (size_t(p.h_colstart[c + 1] - p.h_colstart[c]) + tb - 1)/tb);
+        if (n <= target || tb >= uint32_t(std::max(p.nnzbX, 1))) break;
+    }
+    rt.coltile.assign(size_t(p.nCols) + 1, 0);
+    for (uint32_t c = 0; c < p.nCols; ++c) {
+        uint32_t const b0 = p.h_colstart[c], n = p.h_colstart[c + 1] - b0;
+        uint32_t const nt = std::max<uint32_t>(1, (n + tb - 1)/tb);
+        rt.coltile[c] = uint32_t(rt.tiles.size());
+        for (uint32_t t = 0; t < nt; ++t) {
+            Tile tile; tile.col = c; tile.pad = 0;
+            tile.b0 = b0 + uint32_t((uint64_t(n)*t)/nt);
+            tile.b1 = b0 + uint32_t((uint64_t(n)*(t + 1))/nt);
+            rt.tile_blocks = std::max(rt.tile_blocks, tile.b1 - tile.b0);
+            rt.tiles.push_back(tile);
+        }
+    }
+    rt.coltile[p.nCols] = uint32_t(rt.tiles.size());
+    rt.tile_blocks = std::max<uint32_t>(rt.tile_blocks, 1);
+    return rt;
 }
 
 template <typename real_t, int LM, int LN>
@@ -521,31 +610,43 @@ tfqmrgpuStatus_t launch_resident(Plan &p, cudaStream_t stream, bool dry)
     TFQ_CUDA(cudaGetDevice(&dev));
     TFQ_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     TFQ_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-    if (!coop || 1 != p.gmax || p.nTiles < 1 || p.h_rpA.empty()) return TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED);
+    if (!coop || 1 != p.gmax || p.nnzbX < 1 || p.h_rpA.empty() || p.h_colstart.size() != size_t(p.nCols) + 1)
+        return TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED);
+    ResidentTiling const rt = resident_tiling(p, nsm);
+    uint32_t const nTiles = uint32_t(rt.tiles.size());
+    size_t const tile_blocks = rt.tile_blocks;
     int max_row = 1;                              // entries of a Y block <= blocks in its row of A
     for (int r = 0; r < p.mb; ++r) max_row = std::max(max_row, int(p.h_rpA[r + 1] - p.h_rpA[r]));
     int const max_e = std::min(max_row, 64);
+    int const W = (tile_blocks <= 1) ? 4 : ((tile_blocks <= 2) ? 2 : 1);
     // all tiles co-resident: k CTAs per SM, nsm*k >= nTiles; within that budget keep A in shared memory if it fits with at
-    // least 4 staged entries per warp, and stage as many entries per batch as fit (at most a whole row)
-    int const k = int((p.nTiles + nsm - 1)/nsm);
+    // least 4 staged entries per warp, and stage as many entries per batch as fit (at most a warp's share of a row)
+    int const k = int((nTiles + nsm - 1)/nsm);
     size_t const budget = (size_t(220)*1024)/size_t(k);
-    bool a_res = (max_row <= max_e) && resident_smem<real_t, LM, LN>(p.tile_blocks, max_e, true, std::min(4, max_row)) <= budget;
+    int const share = (max_row + W - 1)/W;
+    bool a_res = (max_row <= max_e) && resident_smem<real_t, LM, LN>(tile_blocks, max_e, true, std::min(4, share)) <= budget;
     char const *const e_ares = std::getenv("TFQMRGPU_RESIDENT_A");           // dev switch: 0 = stage A with X
     if (e_ares && '0' == e_ares[0]) a_res = false;
-    int eb = std::min(max_row, 32);
-    while (eb > 1 && resident_smem<real_t, LM, LN>(p.tile_blocks, max_e, a_res, eb) > budget) --eb;
-    size_t const smem = resident_smem<real_t, LM, LN>(p.tile_blocks, max_e, a_res, eb);
+    int eb = std::min(share, 32);
+    while (eb > 1 && resident_smem<real_t, LM, LN>(tile_blocks, max_e, a_res, eb) > budget) --eb;
+    size_t const smem = resident_smem<real_t, LM, LN>(tile_blocks, max_e, a_res, eb);
     if (smem > budget) return TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED);
     static size_t configured[kMaxDevices] = {0};
     TFQ_CUDA(ensure_dynamic_smem(kernel, smem, configured));
     int per_sm = 0;
     TFQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kResThreads, smem));
-    if (size_t(per_sm)*nsm < p.nTiles) return TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED);
+    if (size_t(per_sm)*nsm < nTiles) return TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED);
     if (dry) return TFQMRGPU_STATUS_SUCCESS;
 
     if (nullptr == p.d_resident_bar) TFQ_CUDA(cudaMalloc((void**)&p.d_resident_bar, 2*sizeof(unsigned)));
     TFQ_CUDA(cudaMemsetAsync(p.d_resident_bar, 0, 2*sizeof(unsigned), stream));
-    if (nullptr == p.d_unit_of_block) {          // one unit per Y block (gmax == 1): storage index of the block -> its unit
+    if (nullptr == p.d_unit_of_block) {          // once per configured plan: tiles, partial-sum scratch, block -> unit
+        TFQ_CUDA(cudaMalloc((void**)&p.d_res_tiles, rt.tiles.size()*sizeof(Tile)));
+        TFQ_CUDA(cudaMalloc((void**)&p.d_res_coltile, rt.coltile.size()*sizeof(uint32_t)));
+        TFQ_CUDA(cudaMalloc((void**)&p.d_res_part, size_t(nTiles)*kPartD*LN*sizeof(double)));
+        TFQ_CUDA(cudaMemcpyAsync(p.d_res_tiles, rt.tiles.data(), rt.tiles.size()*sizeof(Tile), cudaMemcpyHostToDevice, stream));
+        TFQ_CUDA(cudaMemcpyAsync(p.d_res_coltile, rt.coltile.data(), rt.coltile.size()*sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        TFQ_CUDA(cudaStreamSynchronize(stream));                 // (the host vectors are locals)
         TFQ_CUDA(cudaMalloc((void**)&p.d_unit_of_block, std::max<size_t>(p.nnzbX, 1)*sizeof(uint32_t)));
         invert_units_kernel<<<(p.nUnits + 255)/256, 256, 0, stream>>>(p.d_unit_of_block, p.d_unit_y, p.nUnits);
         TFQ_CUDA(cudaGetLastError());
@@ -559,14 +660,15 @@ tfqmrgpuStatus_t launch_resident(Plan &p, cudaStream_t stream, bool dry)
     a.rho = ws<real_t const>(p, p.off_rho); a.beta = ws<real_t const>(p, p.off_beta);
     a.tau = ws<double const>(p, p.off_tau); a.invBn2 = ws<double const>(p, p.off_invBn2);
     a.status = ws<int8_t>(p, p.off_status); a.snap = ws<int8_t>(p, p.off_snap);
-    a.part = ws<double>(p, p.off_part); a.colmon = ws<double>(p, p.off_colmon);
+    a.part = p.d_res_part; a.colmon = ws<double>(p, p.off_colmon);
     a.ctl = ws<Control>(p, p.off_ctl);
-    a.tiles = p.d_tiles; a.coltile = p.d_coltile; a.nCols = p.nCols;
+    a.tiles = p.d_res_tiles; a.coltile = p.d_res_coltile; a.nCols = p.nCols;
     a.unit_e0 = p.d_unit_e0; a.ent_a = p.d_ent_a; a.ent_x = p.d_ent_x; a.unit_of_block = p.d_unit_of_block;
     a.bar = p.d_resident_bar;
-    a.tile_elems = uint32_t(p.tile_blocks*2*size_t(LM)*LN); a.tile_blocks = uint32_t(p.tile_blocks); a.eb = eb;
-    a.max_e = max_e; a.a_resident = a_res ? 1 : 0;
+    a.tile_elems = uint32_t(tile_blocks*2*size_t(LM)*LN); a.tile_blocks = uint32_t(tile_blocks); a.eb = eb;
+    a.max_e = max_e; a.a_resident = a_res ? 1 : 0; a.warps_per_block = W;
     a.trace = nullptr;
+    { char const *const e_abl = std::getenv("TFQMRGPU_RESIDENT_ABLATE"); a.ablate = e_abl ? std::atoi(e_abl) : 0; }
     char const *const e_trace = std::getenv("TFQMRGPU_RESIDENT_TRACE");       // dev: where CTA 0 spends its time
     if (e_trace && '0' != e_trace[0]) {
         if (nullptr == p.d_resident_trace) TFQ_CUDA(cudaMalloc((void**)&p.d_resident_trace, 8*sizeof(unsigned long long)));
@@ -574,13 +676,14 @@ tfqmrgpuStatus_t launch_resident(Plan &p, cudaStream_t stream, bool dry)
         a.trace = p.d_resident_trace;
     }
     void *args[] = { &a };
-    TFQ_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void const*>(kernel), dim3(p.nTiles), dim3(kResThreads), args, smem, stream));
+    TFQ_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void const*>(kernel), dim3(nTiles), dim3(kResThreads), args, smem, stream));
     if (a.trace) {
         unsigned long long h[8];
         TFQ_CUDA(cudaMemcpyAsync(h, a.trace, sizeof(h), cudaMemcpyDeviceToHost, stream));
         TFQ_CUDA(cudaStreamSynchronize(stream));
-        std::printf("# resident: %u CTAs, %zu B shared, eb %d, A resident %d; CTA 0: total %.1f us, barriers %.1f, products %.1f, "
-                    "column sums incl. their barrier %.1f\n", p.nTiles, smem, eb, int(a_res), h[3]*1e-3, h[0]*1e-3, h[1]*1e-3, h[2]*1e-3);
+        std::printf("# resident: %u CTAs of %zu block(s), %d warp(s) per Y block, %zu B shared, eb %d, A resident %d; %llu iterations, %llu probes; CTA 0: total %.1f us, "
+                    "barriers %.1f, products %.1f (staging %.1f, until the sums are done %.1f), column sums incl. their barrier %.1f\n",
+                    nTiles, tile_blocks, W, smem, eb, int(a_res), h[6], h[7], h[3]*1e-3, h[0]*1e-3, h[1]*1e-3, h[4]*1e-3, h[5]*1e-3, h[2]*1e-3);
     }
     return TFQMRGPU_STATUS_SUCCESS;
 }

@@ -97,6 +97,7 @@ struct Plan {
     struct MultiPlan *multi = nullptr;       // in-process multi-GPU plan (multi.cu): this Plan is then only the global analysis
     unsigned *d_resident_bar = nullptr;      // grid barrier of the resident solver (resident.cu)
     unsigned long long *d_resident_trace = nullptr;   // dev: time breakdown of the resident solver (TFQMRGPU_RESIDENT_TRACE)
+    Tile *d_res_tiles = nullptr; uint32_t *d_res_coltile = nullptr; double *d_res_part = nullptr;   // resident solver: its own tiles
     uint32_t *d_unit_of_block = nullptr;     // resident solver: storage index of a Y block -> its unit (plans with gmax == 1)
     size_t tile_blocks = 0;                  // X blocks per vector tile chosen by plan_configure (largest over the block columns)
     int    max_cols_hint = 0;               // ... and choose the product kernel by the unsharded plan's block columns per row
