@@ -119,6 +119,8 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getDevices(tfqmrgpuBsrsvPlan_t plan, int *nDevi
  *     anyway) and reproduces the single-GPU bits of its columns when every block row of X holds the same block columns (a
  *     dense X, the reference's use case); for ragged X patterns the products group a row's entries by the block columns that
  *     share a unit, and results agree to rounding (same iteration count unless a decision falls within that rounding).
+ *     (The bit-for-bit statement is about the per-kernel path; a small system that ONE GPU solves with the resident solver,
+ *     resident.cu, groups its sums by that solver's own tiles and agrees with its shards to rounding.)
  *     tileBlocksHint > 0 forces a tile size (experiments); 0 = the default per-column rule (tfqmrgpux_tileBlocksFor). */
 typedef int32_t (*tfqmrgpuxExchange_t)(void *ctx, double *slots, int count, cudaStream_t stream);
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_setShardExchange(tfqmrgpuBsrsvPlan_t plan, int shard, int nShards, int64_t nRhsGlobal,

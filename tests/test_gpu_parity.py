@@ -651,12 +651,14 @@ def test_simt_switch_gives_fp32_fma_arithmetic(monkeypatch):
 
 
 # ---- RHS-column sharding on one GPU: both ranks' sub-problems solved one after the other, assembled X == 1-GPU X ----
-def test_sharded_solve_reproduces_single_gpu_bits():
-    """tfqmrgpu_b200/sharded.py: with the shard's slice of the 1-GPU cuRAND shadow vector every column
+def test_sharded_solve_reproduces_single_gpu_bits(monkeypatch):
+    """(per-kernel path on both sides: the resident solver of small systems groups its sums by its own tiles)
+    tfqmrgpu_b200/sharded.py: with the shard's slice of the 1-GPU cuRAND shadow vector every column
     follows exactly the 1-GPU arithmetic until its shard stops; shards stop on THEIR columns' convergence (documented
     difference), so compare per shard at the shard's own iteration count via a re-solve with that maxIterations."""
     import torch
     from tfqmrgpu_b200.sharded import ShardedBsrsv, scatter_shards
+    monkeypatch.setenv("TFQMRGPU_RESIDENT", "0")
     prob = P.random_system(12, 8, 8, seed=77, unsorted=True)
     vA = P.interleave(prob.A.val, np.float64); vB = P.interleave(prob.B.val, np.float64).reshape(prob.B.nnzb, -1)
     args = (prob.mb, 8, 8, "z", prob.A.rowptr, prob.A.colind, vA, "n", prob.X.rowptr, prob.X.colind,
@@ -813,9 +815,9 @@ def _one_block_per_row_system(mb, lm, ln, nc, seed):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("which", ["fd", (4, 4, "c", 1), (8, 8, "c", 3), (8, 32, "c", 2), (4, 5, "c", 2), (8, 10, "z", 2), (4, 8, "z", 3),
-                                   (8, 8, "z", 1), (8, 64, "z", 2)], ids=str)
+                                   (8, 8, "z", 1), (8, 64, "z", 2), (4, 4, "c", -5), (8, 8, "c", -3), (8, 8, "z", -2), (4, 8, "z", -4)], ids=str)
 def test_resident_solver_matches_the_per_kernel_path(which, golden, monkeypatch):
-    """Small systems with one X block per block row are solved in ONE cooperative launch (resident.cu: every CTA owns a vector
+    """Small systems of blocks with LM <= 8 are solved in ONE cooperative launch (resident.cu: every CTA owns a vector
     tile in shared memory).  Same status and iteration count (+-1) as the per-kernel path (TFQMRGPU_RESIDENT=0), X equal to
     rounding and to the oracle's, the true residual below the tolerance, and the launch count says which path ran.  Two solves on
     the same plan give the same bits (the barrier state is reset per solve)."""
@@ -823,7 +825,9 @@ def test_resident_solver_matches_the_per_kernel_path(which, golden, monkeypatch)
         prob = P.read_xml(os.path.join(HERE, "golden", "FD_problem.xml")); prec, tol, tA, tB = "z", prob.tolerance, "t", "t"
     else:
         lm, ln, prec, nc = which
-        prob = _one_block_per_row_system(60, lm, ln, nc, seed=lm*10 + ln)
+        # nc < 0: ragged X with up to -nc blocks per block row (units of several block columns, absent partners)
+        prob = _one_block_per_row_system(60, lm, ln, nc, seed=lm*10 + ln) if nc > 0 else \
+               P.random_system(50, lm, ln, ncols=-nc, seed=lm*10 + ln + 1, unsorted=True)
         tol, tA, tB = (1e-9 if prec == "z" else 1e-4), "n", "n"
     dt = np.float64 if prec == "z" else np.float32
     vA = P.interleave(prob.A.val, dt); vB = P.interleave(prob.B.val, dt)

@@ -1,6 +1,7 @@
 # Two ranks, one GPU each, NCCL (launched by tests/test_multi_gpu.py through torchrun): column-sharded solve with the global
 # iteration rule through the exchange hook, X gathered with NCCL, compared on rank 0 with the single-GPU solve.
 import os, sys
+os.environ["TFQMRGPU_RESIDENT"] = "0"      # bit-for-bit comparison of the per-kernel path (the resident solver agrees to rounding)
 import numpy as np
 import torch
 import torch.distributed as dist

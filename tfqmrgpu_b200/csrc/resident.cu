@@ -46,7 +46,8 @@ template <typename real_t> struct ResidentArgs {
     double *part, *colmon;
     Control *ctl;
     Tile const *tiles; uint32_t const *coltile; uint32_t nCols;
-    uint32_t const *unit_e0, *ent_a, *ent_x, *unit_of_block;
+    uint32_t const *unit_e0, *ent_a, *ent_x, *unit_of_block;   // unit_of_block: (unit << 4) | column slot of the Y block in its unit
+    uint32_t gmax;                            // block columns per unit (the entry table holds gmax X blocks per entry)
     unsigned *bar;                            // [0] arrivals, [1] generation
     uint32_t tile_elems;                      // reals per vector tile in shared memory (largest tile)
     uint32_t tile_blocks;                     // blocks of the largest tile
@@ -131,8 +132,8 @@ resident_solve_kernel(ResidentArgs<real_t> const a)
     real_t *const s_alfa = s_rho + 2*LN, *const s_beta = s_alfa + 2*LN, *const s_c67 = s_beta + 2*LN, *const s_eta = s_c67 + 2*LN;
     int8_t *const s_status = reinterpret_cast<int8_t*>(s_eta + 2*LN), *const s_snap = s_status + LN;
     Control *const lc = reinterpret_cast<Control*>((reinterpret_cast<uintptr_t>(s_snap + LN) + 15) & ~uintptr_t(15));
-    uint32_t *const s_e0 = reinterpret_cast<uint32_t*>(lc + 1);                       // [2][tile_blocks] first / end entry of every Y block
-    uint32_t *const s_ea = s_e0 + 2*a.tile_blocks;                                  // [tile_blocks][max_e] A block of an entry
+    uint32_t *const s_e0 = reinterpret_cast<uint32_t*>(lc + 1);                       // [3][tile_blocks] first / end entry, column slot of every Y block
+    uint32_t *const s_ea = s_e0 + 3*a.tile_blocks;                                  // [tile_blocks][max_e] A block of an entry
     uint32_t *const s_ex = s_ea + size_t(a.tile_blocks)*a.max_e;                      // [tile_blocks][max_e] X block (storage index)
     real_t *const s_A = reinterpret_cast<real_t*>((reinterpret_cast<uintptr_t>(s_ex + size_t(a.tile_blocks)*a.max_e) + 15) & ~uintptr_t(15));
     real_t *const s_yp = s_A + (a.a_resident ? size_t(a.tile_blocks)*a.max_e*BA : 0);             // [kResWarps][BE] partial Y blocks
@@ -163,13 +164,15 @@ resident_solve_kernel(ResidentArgs<real_t> const a)
         if (0 == tid) *lc = *a.ctl;
     }
     __syncthreads();
-    // entry lists of the tile's Y blocks (every Y block is its own unit), and the A blocks themselves when they fit
+    // entry lists of the tile's Y blocks (the entries of the block's unit, with the X block of the block's column), and the A blocks
+    // themselves when they fit
     for (int yb = 0; yb < nb; ++yb) {
-        uint32_t const u = a.unit_of_block[t.b0 + yb];
+        uint32_t const ug = a.unit_of_block[t.b0 + yb];
+        uint32_t const u = ug >> 4, g = ug & 15u;
         uint32_t const e0 = a.unit_e0[u], e1 = a.unit_e0[u + 1];
         int const ne = int(min(e1 - e0, uint32_t(a.max_e)));
-        if (0 == tid) { s_e0[yb] = e0; s_e0[a.tile_blocks + yb] = e1; }
-        for (int e = tid; e < ne; e += kResThreads) { s_ea[yb*a.max_e + e] = a.ent_a[e0 + e]; s_ex[yb*a.max_e + e] = a.ent_x[e0 + e]; }
+        if (0 == tid) { s_e0[yb] = e0; s_e0[a.tile_blocks + yb] = e1; s_e0[2*a.tile_blocks + yb] = g; }
+        for (int e = tid; e < ne; e += kResThreads) { s_ea[yb*a.max_e + e] = a.ent_a[e0 + e]; s_ex[yb*a.max_e + e] = a.ent_x[size_t(e0 + e)*a.gmax + g]; }
         if (a.a_resident) {
             float4 *const dst = reinterpret_cast<float4*>(s_A + size_t(yb)*a.max_e*BA);
             for (int q = tid; q < ne*aF4; q += kResThreads)
@@ -250,7 +253,7 @@ resident_solve_kernel(ResidentArgs<real_t> const a)
         for (int yb0 = 0; yb0 < nb; yb0 += groups) {
             int const yb = yb0 + grp;
             if (yb < nb) {
-                uint32_t const e0 = s_e0[yb], e1 = s_e0[a.tile_blocks + yb];
+                uint32_t const e0 = s_e0[yb], e1 = s_e0[a.tile_blocks + yb], gslot = s_e0[2*a.tile_blocks + yb];
                 int const mine = (int(e1 - e0) > ws) ? (int(e1 - e0) - ws + W - 1)/W : 0;     // entries of this warp
                 // KS independent accumulators per output (k = ks mod KS): one warp per scheduler cannot hide the latency of a
                 // chain of dependent fp64 FMAs (measured ~40 cycles each), so the chains are made short and many
@@ -279,7 +282,7 @@ resident_solve_kernel(ResidentArgs<real_t> const a)
                             uint32_t ia = 0, ix = kNoBlock;
                             if (live) {
                                 if (!a.a_resident) ia = (le < a.max_e) ? s_ea[yb*a.max_e + le] : a.ent_a[e0 + le];
-                                ix = (le < a.max_e) ? s_ex[yb*a.max_e + le] : a.ent_x[e0 + le];
+                                ix = (le < a.max_e) ? s_ex[yb*a.max_e + le] : a.ent_x[size_t(e0 + le)*a.gmax + gslot];
                             }
                             #pragma unroll
                             for (int l = 0; l < LPE; ++l) {
@@ -548,9 +551,9 @@ resident_solve_kernel(ResidentArgs<real_t> const a)
     if (0 == blockIdx.x && 0 == tid) { lc->cols_done = 0; *a.ctl = *lc; }
 }
 
-__global__ void invert_units_kernel(uint32_t *unit_of_block, uint32_t const *unit_y, uint32_t nUnits) {
-    uint32_t const u = blockIdx.x*blockDim.x + threadIdx.x;
-    if (u < nUnits) unit_of_block[unit_y[u]] = u;
+__global__ void invert_units_kernel(uint32_t *unit_of_block, uint32_t const *unit_y, uint32_t nUnits, uint32_t gmax) {
+    uint32_t const q = blockIdx.x*blockDim.x + threadIdx.x;
+    if (q < nUnits*gmax) { uint32_t const iy = unit_y[q]; if (kNoBlock != iy) unit_of_block[iy] = ((q / gmax) << 4) | (q % gmax); }
 }
 
 // shared memory of one CTA: tiles of tile_blocks blocks, max_e entries per Y block kept (indices; A blocks if a_res), eb staged
@@ -561,7 +564,7 @@ size_t resident_smem(size_t tile_blocks, int max_e, bool a_res, int eb) {
     size_t const tile_elems = tile_blocks*2*LM*LN;
     size_t b = ((7*tile_elems*sizeof(real_t) + tile_elems*sizeof(float) + 15)/16)*16;
     b += (3*LN + 2*R*LN + 4*LN)*sizeof(double) + 10*LN*sizeof(real_t) + 2*LN + 16 + sizeof(Control);
-    b += (2*tile_blocks + 2*tile_blocks*max_e)*sizeof(uint32_t) + 16;
+    b += (3*tile_blocks + 2*tile_blocks*max_e)*sizeof(uint32_t) + 16;
     if (a_res) b += tile_blocks*max_e*2*LM*LM*sizeof(real_t);
     b += size_t(kResWarps)*2*LM*LN*sizeof(real_t);
     b += size_t(kResWarps)*eb*((a_res ? 0 : 2*LM*LM) + 2*LM*LN)*sizeof(real_t);
@@ -610,7 +613,7 @@ tfqmrgpuStatus_t launch_resident(Plan &p, cudaStream_t stream, bool dry)
     TFQ_CUDA(cudaGetDevice(&dev));
     TFQ_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     TFQ_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-    if (!coop || 1 != p.gmax || p.nnzbX < 1 || p.h_rpA.empty() || p.h_colstart.size() != size_t(p.nCols) + 1)
+    if (!coop || p.gmax < 1 || p.gmax > 16 || p.nUnits >= (1u << 28) || p.nnzbX < 1 || p.h_rpA.empty() || p.h_colstart.size() != size_t(p.nCols) + 1)
         return TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED);
     ResidentTiling const rt = resident_tiling(p, nsm);
     uint32_t const nTiles = uint32_t(rt.tiles.size());
@@ -648,7 +651,7 @@ tfqmrgpuStatus_t launch_resident(Plan &p, cudaStream_t stream, bool dry)
         TFQ_CUDA(cudaMemcpyAsync(p.d_res_coltile, rt.coltile.data(), rt.coltile.size()*sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
         TFQ_CUDA(cudaStreamSynchronize(stream));                 // (the host vectors are locals)
         TFQ_CUDA(cudaMalloc((void**)&p.d_unit_of_block, std::max<size_t>(p.nnzbX, 1)*sizeof(uint32_t)));
-        invert_units_kernel<<<(p.nUnits + 255)/256, 256, 0, stream>>>(p.d_unit_of_block, p.d_unit_y, p.nUnits);
+        invert_units_kernel<<<(p.nUnits*p.gmax + 255)/256, 256, 0, stream>>>(p.d_unit_of_block, p.d_unit_y, p.nUnits, p.gmax);
         TFQ_CUDA(cudaGetLastError());
     }
 
@@ -663,7 +666,7 @@ tfqmrgpuStatus_t launch_resident(Plan &p, cudaStream_t stream, bool dry)
     a.part = p.d_res_part; a.colmon = ws<double>(p, p.off_colmon);
     a.ctl = ws<Control>(p, p.off_ctl);
     a.tiles = p.d_res_tiles; a.coltile = p.d_res_coltile; a.nCols = p.nCols;
-    a.unit_e0 = p.d_unit_e0; a.ent_a = p.d_ent_a; a.ent_x = p.d_ent_x; a.unit_of_block = p.d_unit_of_block;
+    a.unit_e0 = p.d_unit_e0; a.ent_a = p.d_ent_a; a.ent_x = p.d_ent_x; a.unit_of_block = p.d_unit_of_block; a.gmax = p.gmax;
     a.bar = p.d_resident_bar;
     a.tile_elems = uint32_t(tile_blocks*2*size_t(LM)*LN); a.tile_blocks = uint32_t(tile_blocks); a.eb = eb;
     a.max_e = max_e; a.a_resident = a_res ? 1 : 0; a.warps_per_block = W;
@@ -702,8 +705,7 @@ tfqmrgpuStatus_t resident_dispatch(Plan &p, cudaStream_t stream, bool dry)
 
 } // namespace
 
-// Which plans run resident: blocks with LM <= 8 on the SIMT product, one X block per block row (every Y block is its own unit),
-// all vector tiles co-resident with their seven vectors in shared memory (vectors up to ~1.5 MB with 4 KiB tiles), no
+// Which plans run resident: blocks with LM <= 8 on the SIMT product, all vector tiles co-resident with their seven vectors in shared memory (vectors up to ~1.5 MB with 4 KiB tiles), no
 // user-defined operator, no shard exchange, no per-product profiling.  TFQMRGPU_RESIDENT=0 switches it off.
 bool resident_supported(Plan &p)
 {
@@ -712,7 +714,7 @@ bool resident_supported(Plan &p)
     if (e_on && '0' == e_on[0]) return false;
     if (p.use_tc16 || p.use_dmma || p.user_op || p.exch.slots || p.profile || p.multi) return false;
     if ('z' != p.precision && 'c' != p.precision) return false;
-    if (p.LM > 8 || 1 != p.gmax) return false;
+    if (p.LM > 8) return false;
     return TFQMRGPU_STATUS_SUCCESS == resident_dispatch(p, nullptr, true);
 }
 

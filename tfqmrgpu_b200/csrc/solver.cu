@@ -47,6 +47,10 @@ struct TfqRange {
 } // namespace
 
 namespace {
+__global__ void set_control_kernel(Control *ctl, Control const init) { *ctl = init; }
+}
+
+namespace {
 constexpr int kAhead = 3;      // iteration bodies the host may run ahead of the last control read-back
 constexpr int kRing = 6;       // read-back slots; slot 6 = final state, slot 7 = upload staging
 }
@@ -171,7 +175,10 @@ tfqmrgpuStatus_t solve_begin(Plan &p, cudaStream_t stream, double tolerance, int
     c0.tol2 = tolerance*tolerance;
     c0.target_bound2 = c0.tol2*100*100;
     c0.residual2_reached = 1e300;
-    TFQ_CUDA(cudaMemcpyAsync(d_ctl, &c0, sizeof(Control), cudaMemcpyHostToDevice, stream));
+    // by a kernel, not by a host->device copy: a copy would queue on the H2D copy engine behind whatever uploads the caller has in
+    // flight on OTHER streams (the next system's 7 GB operator in a double-buffered caller) and the solve would wait for them
+    set_control_kernel<<<1, 1, 0, stream>>>(d_ctl, c0);
+    TFQ_CUDA(cudaGetLastError());
     TFQ_CUDA(cudaMemsetAsync(p.pBuffer + p.off_ticket, 0, (size_t(p.nCols) + 8)*4, stream));
     // v1 and v4..v9 are contiguous: the initial guess is discarded like in the reference (core.hxx:125)
     TFQ_CUDA(cudaMemsetAsync(p.pBuffer + p.off_v[1], 0, (p.off_v[9] + p.vecBytes) - p.off_v[1], stream));
