@@ -687,6 +687,14 @@ def run_config5(args):
         rows.append(dict(lm=lm, ln=ln, rhs=ncols*ln, prec=prec, tol=tol, status=int(st), iterations=res["iterations"], residual=res["residuum"],
                          solve_ms=ms, gflops=res["flops"]/ms*1e-6, spmm_us=1e3*sp_ms, spmm_gflops=nP*8*lm*lm*ln/sp_ms*1e-6 if sp_ms else 0,
                          kernel="dmma" if info["use_dmma"] else ("tcgen05" if info["use_tc"] else ("simt-small" if info.get("use_small") else "simt")), rank=rank))
+        if int(st) != 0 and prec == "c":
+            # the reference's stopping rule stalled (see the note of this record): the same solve with the opt-in early freeze
+            pl.set_early_freeze(True)
+            pl.solve(tol, maxit)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(); fst = pl.solve(tol, maxit); f1.record(); torch.cuda.synchronize(dev)
+            fres = pl.info()
+            rows[-1]["with_early_freeze"] = dict(status=int(fst), iterations=fres["iterations"], residual=fres["residuum"], solve_ms=f0.elapsed_time(f1))
         pl.close(); h.close(); del sp
         torch.cuda.empty_cache()
     torch.cuda.synchronize(dev)
@@ -707,7 +715,8 @@ def run_config5(args):
                            "all_converged": all(r["status"] == 0 for r in rows),
                            "not_converged": [f"{r['lm']}x{r['ln']} {r['prec']} {r['rhs']} RHS: residual {r['residual']:.1e}" for r in rows if r["status"] != 0],
                            "note": "fp32 rows that end with status 9 (50 iterations) stall in the oracle - the reference's algorithm on the CPU - with the same "
-                                   "shadow vector as well (tests/tools/dev_sweep_diag.py): the residual floor of fp32 tfQMR, not a kernel",
+                                   "shadow vector as well (tests/tools/dev_sweep_diag.py): the residual floor of fp32 tfQMR, not a kernel; "
+                                   "with_early_freeze = the same solve with tfqmrgpux_bsrsv_setEarlyFreeze (opt-in, not reference behaviour)",
                            "rows": rows},
                 "e2e": None, "gpu_launches": None, "roofline": None, "clocks": None}
         if not args.no_cpu and world >= 1:

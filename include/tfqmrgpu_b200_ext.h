@@ -94,6 +94,14 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_setOperator(tfqmrgpuBsrsvPlan_t plan, tfqmrgpux
  * B block becomes the unit block (Re b[j mod LM][j] = 1).  Instead of setMatrix('B'); the reference offers this only to C++ callers
  * of its solve() template. */
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_setRhsTrivial(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan);
+/* Per-right-hand-side early freeze (not in the reference, whose stopping rule wants ALL right-hand sides below the threshold at the
+ * same residual probe, tfqmrgpu_core.hxx:274-298): with on != 0 a right-hand side whose true residual passes a probe keeps its X
+ * from then on (status 2 in getRhsStatus; its updates stop like after a breakdown) while the others continue.  In fp32 with
+ * hundreds of right-hand sides the recurrences of converged columns drift and the reference's rule may not be met at one probe;
+ * the freeze keeps what was reached.  (It cannot help a right-hand side that never passes: the two fp32 cases of the block-size sweep that
+ * stall at a residual of 2e-2 - in the oracle as well - stall with it too.)  Default off = the reference's behaviour.  Takes effect with
+ * the next solve. */
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setEarlyFreeze(tfqmrgpuBsrsvPlan_t plan, int on);
 
 /* ---- several GPUs: the independent right-hand-side block columns of X/B are sharded, A is replicated --------
  *

@@ -882,3 +882,33 @@ def test_resident_solver_max_iterations_and_breakdown(monkeypatch):
         assert res["0"][1] == res["1"][1] and np.array_equal(res["0"][2], res["1"][2])
         assert res["1"][3] == 3 and res["0"][3] > 3
     pl.close(); h.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", ["0", "1"])
+def test_early_freeze_extension(resident, monkeypatch):
+    """tfqmrgpux_bsrsv_setEarlyFreeze (opt-in): off = the reference's rule (bit-identical to a plan that never heard of
+    it); on = right-hand sides whose true residual passed a probe keep their X (status 2) and the solve ends with every residual below
+    the threshold, never later than without it.  fp32 with many right-hand sides is where the reference's rule stalls."""
+    monkeypatch.setenv("TFQMRGPU_RESIDENT", resident)
+    from tfqmrgpu_b200 import synthetic
+    lm, ln, ncols, tol, maxit = 4, 5, 40, 2e-3, 40
+    sp = synthetic.Stencil27(5, lm, ln, ncols, sigma=8.0, dtype=np.float32, device="cuda")
+    res = {}
+    for mode in ("never", "off", "on"):
+        h = api.Handle(); pl = api.BsrsvPlan(h, sp.mb, sp.rpA, sp.ciA, sp.rpX, sp.ciX, sp.rpB, sp.ciB)
+        pl.buffer_size_for(lm, ln, "c"); pl.set_buffer()
+        pl.set_matrix("A", sp.valA_host.numpy()); pl.set_matrix("B", sp.valB)
+        if mode != "never":
+            pl.set_early_freeze(mode == "on")
+        st = pl.solve(tol, maxit)
+        res[mode] = (st, pl.info(), pl.rhs_status().copy(), pl.get_matrix("X").copy())
+        pl.close(); h.close()
+    assert res["never"][0] == res["off"][0] and res["never"][1]["iterations"] == res["off"][1]["iterations"]
+    assert np.array_equal(res["never"][3], res["off"][3]) and np.array_equal(res["never"][2], res["off"][2])
+    st, info, rhs, X = res["on"]
+    assert st == 0 and info["residuum"] <= tol
+    assert info["iterations"] <= res["off"][1]["iterations"]
+    assert set(np.unique(rhs)) <= {0, 2}
+    if res["off"][0] == 0:      # both converged: the frozen solution is as good as the reference rule's to the threshold
+        assert np.abs(X - res["off"][3]).max() <= 50*tol*np.abs(res["off"][3]).max()

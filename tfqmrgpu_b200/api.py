@@ -283,6 +283,10 @@ class BsrsvPlan:
                                                      trans.encode(), layout, int(part), int(n_parts), info), "setMatrixPart")
         return dict(off=int(info[0]), length=int(info[1]), scale_off=int(info[2]), scale_length=int(info[3]), block0=int(info[4]), nblocks=int(info[5]))
 
+    def set_early_freeze(self, on=True):
+        """Opt-in (not in the reference): a right-hand side whose true residual passes a probe keeps its X (status 2)."""
+        _check(self.lib.tfqmrgpux_bsrsv_setEarlyFreeze(self.plan, int(bool(on))), "setEarlyFreeze")
+
     def set_rhs_trivial(self):
         """B := unit blocks (the reference's rhs_trivial right-hand sides) instead of set_matrix('B', ...)."""
         _check(self.lib.tfqmrgpux_bsrsv_setRhsTrivial(self.handle.h, self.plan), "setRhsTrivial")

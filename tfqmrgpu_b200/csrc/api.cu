@@ -700,6 +700,13 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_setRhsTrivial(tfqmrgpuHandle_t handle, tfqmrgpu
     if (nullptr == p.pBuffer || !p.configured) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     return launch_unit_rhs(p, static_cast<Handle*>(handle)->stream);
 }
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setEarlyFreeze(tfqmrgpuBsrsvPlan_t plan, int on) {
+    if (nullptr == plan) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan &p = *P(plan);
+    p.early_freeze = on ? 1 : 0;
+    if (p.multi) multi_set_early_freeze(p);
+    return TFQMRGPU_STATUS_SUCCESS;
+}
 tfqmrgpuStatus_t tfqmrgpux_tileBlocksFor(int64_t nnzbX, int64_t blockBytes, int64_t *tileBlocks) {
     if (nullptr == tileBlocks || nnzbX < 0 || blockBytes < 1) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     int dev = 0, nsm = 148;

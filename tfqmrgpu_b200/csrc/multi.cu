@@ -451,6 +451,12 @@ size_t multi_off_gx(Plan const &p) { return p.multi->off_gx; }
 size_t multi_off_scratch(Plan const &p) { return p.multi->off_scratch; }
 
 // per right-hand-side status in the unsharded (block column, lane) order
+void multi_set_early_freeze(Plan &p)
+{
+    if (nullptr == p.multi) return;
+    for (auto &sh : p.multi->shards) if (sh.plan) sh.plan->early_freeze = p.early_freeze;
+}
+
 tfqmrgpuStatus_t multi_rhs_status(Plan &p, int8_t *statusHost)
 {
     MultiPlan &m = *p.multi;

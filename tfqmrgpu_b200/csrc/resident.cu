@@ -312,38 +312,16 @@ resident_solve_kernel(ResidentArgs<real_t> const a)
                             real_t const *const Xs = reinterpret_cast<real_t const*>(st4 + size_t(e)*perE + (perE - xF4));
                             real_t const *const As = a.a_resident ? (s_A + (size_t(yb)*a.max_e + le)*BA)
                                                                   : reinterpret_cast<real_t const*>(st4 + size_t(e)*perE);
-                            if constexpr (LM*TJ <= 16) {
-                                // all operands of the entry into registers first: one shared-memory latency per entry instead of
-                                // one per k (a lone warp per scheduler has nothing else to issue while it waits)
-                                real_t ar[LM], ai[LM], xr[LM][TJ], xi[LM][TJ];
+                            #pragma unroll
+                            for (int k = 0; k < LM; ++k) {
+                                real_t const ar = As[k*LM + i], ai = As[LM*LM + k*LM + i];
                                 #pragma unroll
-                                for (int k = 0; k < LM; ++k) {
-                                    ar[k] = As[k*LM + i]; ai[k] = As[LM*LM + k*LM + i];
-                                    #pragma unroll
-                                    for (int jj = 0; jj < TJ; ++jj) { xr[k][jj] = Xs[k*LN + jg*TJ + jj]; xi[k][jj] = Xs[PL + k*LN + jg*TJ + jj]; }
-                                }
-                                #pragma unroll
-                                for (int k = 0; k < LM; ++k) {
-                                    #pragma unroll
-                                    for (int jj = 0; jj < TJ; ++jj) {
-                                        acr[k % KS][jj] = fma( ar[k], xr[k][jj], acr[k % KS][jj]);   // complex multiply-accumulate (blockmult.hxx:76-77)
-                                        acr[k % KS][jj] = fma(-ai[k], xi[k][jj], acr[k % KS][jj]);
-                                        aci[k % KS][jj] = fma( ar[k], xi[k][jj], aci[k % KS][jj]);
-                                        aci[k % KS][jj] = fma( ai[k], xr[k][jj], aci[k % KS][jj]);
-                                    }
-                                }
-                            } else {
-                                #pragma unroll
-                                for (int k = 0; k < LM; ++k) {
-                                    real_t const ar = As[k*LM + i], ai = As[LM*LM + k*LM + i];
-                                    #pragma unroll
-                                    for (int jj = 0; jj < TJ; ++jj) {
-                                        real_t const xr = Xs[k*LN + jg*TJ + jj], xi = Xs[PL + k*LN + jg*TJ + jj];
-                                        acr[k % KS][jj] = fma( ar, xr, acr[k % KS][jj]);
-                                        acr[k % KS][jj] = fma(-ai, xi, acr[k % KS][jj]);
-                                        aci[k % KS][jj] = fma( ar, xi, aci[k % KS][jj]);
-                                        aci[k % KS][jj] = fma( ai, xr, aci[k % KS][jj]);
-                                    }
+                                for (int jj = 0; jj < TJ; ++jj) {
+                                    real_t const xr = Xs[k*LN + jg*TJ + jj], xi = Xs[PL + k*LN + jg*TJ + jj];
+                                    acr[k % KS][jj] = fma( ar, xr, acr[k % KS][jj]);         // complex multiply-accumulate (blockmult.hxx:76-77)
+                                    acr[k % KS][jj] = fma(-ai, xi, acr[k % KS][jj]);
+                                    aci[k % KS][jj] = fma( ar, xi, aci[k % KS][jj]);
+                                    aci[k % KS][jj] = fma( ai, xr, aci[k % KS][jj]);
                                 }
                             }
                         }
@@ -544,6 +522,8 @@ resident_solve_kernel(ResidentArgs<real_t> const a)
                 else if (res2 <= 0) {           // core.hxx:282-285: the component counts as converged
                     if (s_status[tid] == s_snap[tid]) s_status[tid] = 1;
                     s_snap[tid] = 1;
+                } else if (lc->freeze && 0 == s_snap[tid] && 0 == s_status[tid]) {
+                    s_status[tid] = kFrozen; s_snap[tid] = kFrozen;     // early-freeze extension (vec_body.cuh)
                 }
                 s_mon[tid] = res2; s_mon[LN + tid] = notdone;
             }

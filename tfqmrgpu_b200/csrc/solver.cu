@@ -175,6 +175,7 @@ tfqmrgpuStatus_t solve_begin(Plan &p, cudaStream_t stream, double tolerance, int
     c0.tol2 = tolerance*tolerance;
     c0.target_bound2 = c0.tol2*100*100;
     c0.residual2_reached = 1e300;
+    c0.freeze = p.early_freeze;
     // by a kernel, not by a host->device copy: a copy would queue on the H2D copy engine behind whatever uploads the caller has in
     // flight on OTHER streams (the next system's 7 GB operator in a double-buffered caller) and the solve would wait for them
     set_control_kernel<<<1, 1, 0, stream>>>(d_ctl, c0);

@@ -38,7 +38,7 @@ struct Control {
     int      result;             // 0 converged, 9 max iterations, 6 breakdown (core.hxx:170,258,297)
     int      iterations_needed;  // core.hxx:171,295
     unsigned cols_done;          // ticket of the cross-column finalisation
-    int      pad_;
+    int      freeze;             // tfqmrgpux_bsrsv_setEarlyFreeze: a right-hand side whose true residual passed a probe keeps its X (status 2)
     double   tol2;               // core.hxx:129
     double   target_bound2;      // core.hxx:130,290
     double   residual2_reached;  // core.hxx:131,287
@@ -95,6 +95,7 @@ struct Plan {
     bool use_dmma = false;            // complex fp64 product on the FP64 tensor pipe (spmm_dmma.cu)
     Exchange exch;
     struct MultiPlan *multi = nullptr;       // in-process multi-GPU plan (multi.cu): this Plan is then only the global analysis
+    int early_freeze = 0;                    // opt-in: freeze converged right-hand sides at the probes (tfqmrgpux_bsrsv_setEarlyFreeze)
     unsigned *d_resident_bar = nullptr;      // grid barrier of the resident solver (resident.cu)
     unsigned long long *d_resident_trace = nullptr;   // dev: time breakdown of the resident solver (TFQMRGPU_RESIDENT_TRACE)
     Tile *d_res_tiles = nullptr; uint32_t *d_res_coltile = nullptr; double *d_res_part = nullptr;   // resident solver: its own tiles
@@ -176,6 +177,7 @@ tfqmrgpuStatus_t multi_gather_x(Plan &p, cudaStream_t homeStream);
 size_t multi_off_gx(Plan const &p);
 size_t multi_off_scratch(Plan const &p);
 tfqmrgpuStatus_t multi_rhs_status(Plan &p, int8_t *statusHost);
+void multi_set_early_freeze(Plan &p);
 
 // ---- kernels' host launchers --------------------------------------------------------------------
 // block-sparse product y = A*x on storage-ordered vectors; gate: run only if ctl->state == expect (expect < 0: always)

@@ -12,6 +12,9 @@ namespace tfq {
 namespace {
 
 constexpr double kEpsilon = 2.5e-308; // linalg.hxx:31
+// Early-freeze extension (not in the reference): status of a right-hand side whose true residual passed a probe;
+// its X is kept from then on (eta = 0 like after a breakdown) while the other right-hand sides continue.
+constexpr int8_t kFrozen = 2;
 
 template <typename real_t> struct VecArgs {
     real_t *v1, *v4, *v5, *v6, *v7, *v8, *v9;
@@ -47,7 +50,7 @@ __device__ __forceinline__ void dec35(VecArgs<real_t> const &a, uint32_t c, int 
     double const abs2rho = rho_Re*rho_Re + rho_Im*rho_Im;
     double const abs2z = z_Re*z_Re + z_Im*z_Im;
     if ((abs2z < kEpsilon) || (abs2rho < kEpsilon)) {
-        a.status[size_t(c)*a.LN + j] = -1;
+        if (kFrozen != a.status[size_t(c)*a.LN + j]) a.status[size_t(c)*a.LN + j] = -1;
         a.beta[r] = 0; a.beta[m] = 0; a.rho[r] = 0; a.rho[m] = 0;
     } else {
         double const den = 1./abs2rho;
@@ -64,7 +67,7 @@ __device__ __forceinline__ void dec34(VecArgs<real_t> const &a, uint32_t c, int 
     double const abs2rho = rho_Re*rho_Re + rho_Im*rho_Im;
     double const abs2z = z_Re*z_Re + z_Im*z_Im;
     if ((abs2z < kEpsilon) || (abs2rho < kEpsilon)) {
-        a.status[size_t(c)*a.LN + j] = -2;
+        if (kFrozen != a.status[size_t(c)*a.LN + j]) a.status[size_t(c)*a.LN + j] = -2;
         a.alfa[r] = 0; a.alfa[m] = 0; a.c67[r] = 0; a.c67[m] = 0;
     } else {
         double const eta_Re = double(a.eta[r]), eta_Im = double(a.eta[m]);
@@ -92,10 +95,10 @@ __device__ __forceinline__ void decT(VecArgs<real_t> const &a, uint32_t c, int j
         a.tau[s] = D55*cosi;
         r67 = real_t(Var*cosi);
     } else {
-        a.status[s] = -3;
+        if (kFrozen != a.status[s]) a.status[s] = -3;
         a.var[s] = 0; a.tau[s] = 0;
     }
-    if (a.status[s] < 0) { a.eta[r] = 0; a.eta[m] = 0; }
+    if (a.status[s] < 0 || kFrozen == a.status[s]) { a.eta[r] = 0; a.eta[m] = 0; }   // (frozen: only with the early-freeze extension)
     else { a.eta[r] = real_t(-cosi*double(a.alfa[r])); a.eta[m] = real_t(-cosi*double(a.alfa[m])); }
     if (with_c67) { a.c67[r] = r67; a.c67[m] = 0; }
 }
@@ -448,6 +451,8 @@ __device__ __forceinline__ void vec_tile(VecArgs<real_t> const &a, uint32_t cons
                 // the fused dec35 of the NEXT iteration has already run; keep its verdict if it changed the status
                 if (a.status[s] == a.snap[s]) a.status[s] = 1;
                 a.snap[s] = 1;              // snap = the reference's status_h (what getRhsStatus reports)
+            } else if (a.ctl->freeze && 0 == a.snap[s] && 0 == a.status[s]) {
+                a.status[s] = kFrozen; a.snap[s] = kFrozen;     // early-freeze extension: this right-hand side is done
             }
             mon[j] = res2; mon[LN + j] = notdone;
         }
