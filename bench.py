@@ -188,10 +188,10 @@ def _make_plan(torch, api, sp, lm, ln, prec, dev, stream=None, shard=None):
     pl.create_plan_ms = 1e3*(time.perf_counter() - t0)          # plan analysis on the device (createPlan), host -> host
     keep = None
     if shard is not None:
-        dist, rank, world, ncols_global = shard
-        es = 8 if prec == "z" else 4
+        dist, rank, world, ncols_global = shard[:4]
+        group = shard[4] if len(shard) > 4 else None
         pl.set_shard_hints(0, ncols_global)
-        keep = sharded.NcclExchange(pl, dist, rank, world, ncols_global*ln, dev)
+        keep = sharded.NcclExchange(pl, dist, rank, world, ncols_global*ln, dev, group=group)
     t0 = time.perf_counter()
     nbytes = pl.buffer_size_for(lm, ln, prec)
     torch.cuda.synchronize(dev)
@@ -239,7 +239,10 @@ def run_ours(args):
     ncols_global = world*ncols
     sp = synthetic.Stencil27(n, lm, ln, ncols, sigma=args.sigma, dtype=dt, device=dev, col0=rank*ncols, ncols_global=ncols_global,
                              with_values=False)
-    shard = (dist, rank, world, ncols_global) if world > 1 else None
+    # the exchange of the convergence monitors gets its own communicator: the broadcasts that distribute the NEXT system's operator
+    # (default group, other stream) are issued before a solve and would otherwise be ahead of its all-gathers in the same queue
+    ex_group = dist.new_group(backend="nccl") if world > 1 else None
+    shard = (dist, rank, world, ncols_global, ex_group) if world > 1 else None
     h, pl, ws_t, base, nbytes = _make_plan(torch, api, sp, lm, ln, prec, dev, shard=shard)
     info = pl.plan_info()
     create_plan_ms, configure_ms = pl.create_plan_ms, pl.configure_ms
@@ -252,7 +255,14 @@ def run_ours(args):
     x_host = torch.empty(sp.nnzbX*lm*ln*2, dtype=torch.float64 if prec == "z" else torch.float32).pin_memory()
     x_np = x_host.numpy()
 
-    def upload(pl=pl, ws_t=ws_t, base=base, stream=None):
+    def upload(pl=pl, ws_t=ws_t, base=base, stream=None, after=None):
+        """A (this rank's row range, then the exchange of the converted ranges) and B of one system, asynchronously on the plan's
+        stream.  after: an event of the previous upload - two host->device copies in flight on two streams SHARE the PCIe link
+        and both finish late (measured: two 7.25 GB uploads enqueued together both end after 272 ms instead of 131 and 262), so
+        a pipelined caller chains its uploads.  Returns the event that marks this upload done."""
+        s_up = stream if stream is not None else torch.cuda.current_stream(dev)
+        if after is not None:
+            s_up.wait_event(after)
         pl.set_matrix_part(valA_part.data_ptr(), rank, world)
         if world > 1:
             with torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream(dev)):
@@ -262,6 +272,9 @@ def run_ours(args):
                     if q["scale_length"]:
                         dist.broadcast(ws_t[base + q["scale_off"]:base + q["scale_off"] + q["scale_length"]], src=r)
         pl.set_matrix("B", None, "n", raw_ptr=valB.data_ptr())
+        done = torch.cuda.Event()
+        done.record(s_up)
+        return done
 
     upload()
     statuses = []
@@ -331,20 +344,31 @@ def run_ours(args):
     if pipelined:
         upload(*lanes[1][:4]); pl2.solve(tol, maxit)        # untimed warm-up of the second plan (graph capture, first touch)
     e2e_flops = 0
+    timeline = [] if os.environ.get("TFQMRGPU_BENCH_TIMELINE") else None      # dev: when did every upload finish on the device?
+
+    def mark(lane_stream, what):
+        if timeline is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(lane_stream if lane_stream is not None else torch.cuda.current_stream(dev))
+            timeline.append((what, ev, 1e3*(time.perf_counter() - t0)))
     barrier()
+    base_ev = torch.cuda.Event(enable_timing=True); base_ev.record()
     t0 = time.perf_counter()
-    upload(*lanes[0][:4])
+    last_up = upload(*lanes[0][:4]); mark(lanes[0][3], "upload 0 done")
     for k in range(args.steps):
         if pipelined and k + 1 < args.steps:
-            upload(*lanes[(k + 1) % 2][:4])
+            last_up = upload(*lanes[(k + 1) % 2][:4], after=last_up); mark(lanes[(k + 1) % 2][3], f"upload {k + 1} done")
         elif not pipelined and k > 0:
             upload(*lanes[0][:4])
-        cur, _, _, _, xout = lanes[k % len(lanes)]
-        cur.solve(tol, maxit)
-        cur.get_matrix("X", "n", L.LAYOUT_RIRIRIRI, out=xout)
+        cur, _, _, lane_stream, xout = lanes[k % len(lanes)]
+        cur.solve(tol, maxit); mark(lane_stream, f"solve {k} done")
+        cur.get_matrix("X", "n", L.LAYOUT_RIRIRIRI, out=xout); mark(lane_stream, f"download {k} done")
         e2e_flops += cur.info()["flops"]
     torch.cuda.synchronize(dev)
     e2e_s = reduce_max(time.perf_counter() - t0)
+    if timeline is not None and rank == 0:
+        for what, ev, host_ms in timeline:
+            print(f"timeline: {what:18s} device {base_ev.elapsed_time(ev):8.1f} ms   (host enqueued at {host_ms:8.1f} ms)", file=sys.stderr)
     e2e_total = reduce_sum(e2e_flops)
     # one unpipelined step for comparison (upload -> solve -> download, nothing overlapped)
     barrier()
@@ -400,7 +424,7 @@ def run_ours(args):
         sc_global = args.strong_rhs//ln
         sc = sc_global//world
         sp2 = synthetic.Stencil27(n, lm, ln, sc, sigma=args.sigma, dtype=dt, device=dev, col0=rank*sc, ncols_global=sc_global, with_values=False)
-        hs, ps, wss, bases, nbs = _make_plan(torch, api, sp2, lm, ln, prec, dev, shard=(dist, rank, world, sc_global) if world > 1 else None)
+        hs, ps, wss, bases, nbs = _make_plan(torch, api, sp2, lm, ln, prec, dev, shard=(dist, rank, world, sc_global, ex_group) if world > 1 else None)
         parts2 = [ps.matrix_part_info(r, world) for r in range(world)]
         assert parts2[rank]["block0"] == mine["block0"] and parts2[rank]["nblocks"] == mine["nblocks"]
         ps.set_matrix_part(valA_keep.data_ptr(), rank, world)
@@ -449,7 +473,7 @@ def run_ours(args):
             "e2e": {"value": e2e_total/e2e_s*1e-9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "a_distribution": (f"every rank uploads 1/{world} of A over its own PCIe link, converted ranges exchanged with NCCL broadcasts over NVLink"
                                        if world > 1 else "H2D"),
-                    "ms_per_step": 1e3*e2e_s/args.steps, "pipelining": "2 plans: upload of step k+1 overlaps solve of step k" if pipelined else "none (second workspace not available)",
+                    "ms_per_step": 1e3*e2e_s/args.steps, "pipelining": "2 plans: upload of step k+1 (chained after upload k) overlaps solve of step k" if pipelined else "none (second workspace not available)",
                     "ms_single_step_unpipelined": 1e3*e2e_serial_s},
             "gpu_launches": int(launches),
             "roofline": roofline,

@@ -267,6 +267,47 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_getBuffer(tfqmrgpuHandle_t, tfqmrgpuBsrsvPlan_t 
     return TFQMRGPU_STATUS_SUCCESS;
 }
 
+// Blocks [b0, b0 + nb) of A: host -> device into the A window and layout conversion in place (+ the block maxima for the row scales of the
+// fp16-pair operand, xop.cu).  valBlocks points to the first of these blocks in the caller's host array.  Large ranges go in chunks on
+// a copy stream while the layout kernel converts the previous chunk on the caller's stream: the conversion hides behind the PCIe transfer.
+static tfqmrgpuStatus_t upload_a_blocks(Plan &p, cudaStream_t stream, void const *valBlocks, uint32_t b0, uint32_t nb, bool is_double,
+                                        tfqmrgpuDataLayout_t layout, bool trans, double scal_imag)
+{
+    size_t const s = is_double ? 8 : 4;
+    size_t const blockBytes = 2*size_t(p.LM)*p.LM*s, bytes = size_t(nb)*blockBytes;
+    char *const dst = p.pBuffer + p.off_A + size_t(b0)*blockBytes;
+    size_t const chunkBytes = size_t(256) << 20;
+    auto converted = [&](uint32_t c0, uint32_t cn) -> tfqmrgpuStatus_t {      // blocks [b0 + c0, b0 + c0 + cn)
+        tfqmrgpuStatus_t const cst = convert_inplace(p, dst + size_t(c0)*blockBytes, cn, p.LM, p.LM, is_double, layout, trans, scal_imag, stream);
+        if (cst || !p.use_tc16) return cst;
+        return launch_aop_blockmax(p, b0 + c0, cn, stream);
+    };
+    if (bytes <= chunkBytes) {
+        TFQ_CUDA(cudaMemcpyAsync(dst, valBlocks, bytes, cudaMemcpyHostToDevice, stream));
+        return converted(0, nb);
+    }
+    if (nullptr == p.copy_stream) TFQ_CUDA(cudaStreamCreateWithFlags(&p.copy_stream, cudaStreamNonBlocking));
+    if (nullptr == p.chunk_ev[0]) {
+        for (auto &e : p.chunk_ev) TFQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    TFQ_CUDA(cudaEventRecord(p.chunk_ev[0], stream));        // earlier work on the caller's stream may still read A (or must precede the upload)
+    TFQ_CUDA(cudaStreamWaitEvent(p.copy_stream, p.chunk_ev[0], 0));
+    uint32_t const blocksPerChunk = uint32_t(chunkBytes/blockBytes);
+    tfqmrgpuStatus_t cst = TFQMRGPU_STATUS_SUCCESS;
+    int turn = 0;
+    for (uint32_t c0 = 0; c0 < nb && TFQMRGPU_STATUS_SUCCESS == cst; c0 += blocksPerChunk, ++turn) {
+        uint32_t const cn = std::min(blocksPerChunk, nb - c0);
+        size_t const off = size_t(c0)*blockBytes;
+        TFQ_CUDA(cudaMemcpyAsync(dst + off, static_cast<char const*>(valBlocks) + off, size_t(cn)*blockBytes, cudaMemcpyHostToDevice, p.copy_stream));
+        // (re-recording an event that a stream still waits for is fine: the wait took the earlier record)
+        cudaEvent_t const ev = p.chunk_ev[1 + (turn & 1)];
+        TFQ_CUDA(cudaEventRecord(ev, p.copy_stream));
+        TFQ_CUDA(cudaStreamWaitEvent(stream, ev, 0));
+        cst = converted(c0, cn);
+    }
+    return cst;
+}
+
 // ---- setMatrix / getMatrix: tfqmrgpu.cu:467-645 -----------------------------------------------------
 tfqmrgpuStatus_t tfqmrgpu_bsrsv_setMatrix(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, char const var, void const *val,
     char const precision, int const, int const, char const transposition, tfqmrgpuDataLayout_t const layout)
@@ -293,43 +334,8 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_setMatrix(tfqmrgpuHandle_t handle, tfqmrgpuBsrsv
     if (('z' == lower(precision)) != is_double) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, precision); // tfqmrgpu.cu:538-542
     if (p.multi) return multi_set_matrix(p, v, val, precision, transposition, layout, trans, scal_imag);
     if ('a' == v) {
-        char *const dst = p.pBuffer + p.off_A;
-        size_t const blockBytes = 2*size_t(p.LM)*p.LM*s, bytes = size_t(nnzb)*blockBytes;
-        size_t const chunkBytes = size_t(256) << 20;
-        // after the layout conversion of a chunk: block maxima for the row scales of the fp16-pair operand (xop.cu)
-        auto converted = [&](uint32_t b0, uint32_t nb) -> tfqmrgpuStatus_t {
-            tfqmrgpuStatus_t const cst = convert_inplace(p, dst + size_t(b0)*blockBytes, nb, p.LM, p.LM, is_double, layout, trans, scal_imag, stream);
-            if (cst || !p.use_tc16) return cst;
-            return launch_aop_blockmax(p, b0, nb, stream);
-        };
-        if (bytes <= chunkBytes) {
-            TFQ_CUDA(cudaMemcpyAsync(dst, val, bytes, cudaMemcpyHostToDevice, stream));
-            tfqmrgpuStatus_t const cst = converted(0, nnzb);
-            if (cst || !p.use_tc16) return cst;
-            return launch_aop_convert(p, stream);
-        }
-        // large operator: upload in chunks on a copy stream while the layout kernel converts the previous chunk on the
-        // caller's stream (the conversion then hides completely behind the PCIe transfer)
-        if (nullptr == p.copy_stream) TFQ_CUDA(cudaStreamCreateWithFlags(&p.copy_stream, cudaStreamNonBlocking));
-        if (nullptr == p.chunk_ev[0]) {
-            for (auto &e : p.chunk_ev) TFQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        }
-        TFQ_CUDA(cudaEventRecord(p.chunk_ev[0], stream));        // earlier work on the caller's stream may still read A
-        TFQ_CUDA(cudaStreamWaitEvent(p.copy_stream, p.chunk_ev[0], 0));
-        uint32_t const blocksPerChunk = uint32_t(chunkBytes/blockBytes);
-        tfqmrgpuStatus_t cst = TFQMRGPU_STATUS_SUCCESS;
-        int turn = 0;
-        for (uint32_t b0 = 0; b0 < nnzb && TFQMRGPU_STATUS_SUCCESS == cst; b0 += blocksPerChunk, ++turn) {
-            uint32_t const nb = std::min(blocksPerChunk, nnzb - b0);
-            size_t const off = size_t(b0)*blockBytes;
-            TFQ_CUDA(cudaMemcpyAsync(dst + off, static_cast<char const*>(val) + off, size_t(nb)*blockBytes, cudaMemcpyHostToDevice, p.copy_stream));
-            // (re-recording an event that a stream still waits for is fine: the wait took the earlier record)
-            cudaEvent_t const ev = p.chunk_ev[1 + (turn & 1)];
-            TFQ_CUDA(cudaEventRecord(ev, p.copy_stream));
-            TFQ_CUDA(cudaStreamWaitEvent(stream, ev, 0));
-            cst = converted(b0, nb);
-        }
-        if (cst || !p.use_tc16) return cst;
+        st = upload_a_blocks(p, stream, val, 0, nnzb, is_double, layout, trans, scal_imag);
+        if (st || !p.use_tc16) return st;
         return launch_aop_convert(p, stream);
     }
     if ('b' == v) {
@@ -685,11 +691,8 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_setMatrixPart(tfqmrgpuHandle_t handle, tfqmrgpu
     if (info[5] < 1) return TFQMRGPU_STATUS_SUCCESS;
     if (nullptr == valPart) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     cudaStream_t const stream = static_cast<Handle*>(handle)->stream;
-    char *const dst = p.pBuffer + info[0];
     uint32_t const b0 = uint32_t(info[4]), nb = uint32_t(info[5]);
-    TFQ_CUDA(cudaMemcpyAsync(dst, valPart, size_t(info[1]), cudaMemcpyHostToDevice, stream));
-    st = convert_inplace(p, dst, nb, p.LM, p.LM, is_double, layout, trans, scal_imag, stream);
-    if (TFQMRGPU_STATUS_SUCCESS == st && p.use_tc16) st = launch_aop_blockmax(p, b0, nb, stream);
+    st = upload_a_blocks(p, stream, valPart, b0, nb, is_double, layout, trans, scal_imag);
     if (TFQMRGPU_STATUS_SUCCESS == st && p.use_tc16) st = launch_aop_convert_rows(p, row0, row1, stream);
     return st;
 }

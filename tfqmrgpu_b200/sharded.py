@@ -91,7 +91,10 @@ class NcclExchange:
     the other shards' convergence monitors it calls back, and the ranks all-gather ``world`` blocks of 4 doubles on the solver's
     stream with NCCL (``torch.distributed``).  Keep the object alive as long as the plan solves."""
 
-    def __init__(self, plan, dist, rank, world, n_rhs_global, device):
+    def __init__(self, plan, dist, rank, world, n_rhs_global, device, group=None):
+        """group: the process group (communicator) of the exchange.  Give it its own one (dist.new_group()) when other collectives of
+        the caller - e.g. the distribution of the next system's operator - may be in flight on other streams: operations on ONE NCCL
+        communicator execute in issue order, and the solve would wait behind them."""
         import torch
         self.slots = torch.zeros(2*2*world*4, dtype=torch.float64, device=device)
         self.mine = torch.zeros(4, dtype=torch.float64, device=device)
@@ -107,7 +110,7 @@ class NcclExchange:
             ext = torch.cuda.ExternalStream(stream, device=device) if stream else torch.cuda.default_stream(device)
             with torch.cuda.stream(ext):
                 self.mine.copy_(view[4*rank:4*rank + 4])
-                dist.all_gather_into_tensor(view, self.mine)
+                dist.all_gather_into_tensor(view, self.mine, group=group)
             self.calls += 1
             self.cpu_s += time.perf_counter() - t0
             return 0
