@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29540"
+timeout 500 $T bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err
+echo "n8 rc=$?"
+tail -c 300 gpurun_out/bench_n8.json
