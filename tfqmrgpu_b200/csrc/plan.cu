@@ -368,6 +368,7 @@ static void free_configured(Plan &p) {
     cudaFree(p.d_cta_u0); p.d_cta_u0 = nullptr;
     cudaFree(p.d_unit_row); p.d_unit_row = nullptr;
     cudaFree(p.d_unit_of_block); p.d_unit_of_block = nullptr;
+    p.resident_fits = -1;
     cudaFree(p.d_res_tiles); p.d_res_tiles = nullptr;
     cudaFree(p.d_res_coltile); p.d_res_coltile = nullptr;
     cudaFree(p.d_res_part); p.d_res_part = nullptr;

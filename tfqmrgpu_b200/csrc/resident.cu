@@ -620,6 +620,15 @@ tfqmrgpuStatus_t launch_resident(Plan &p, cudaStream_t stream, bool dry)
     ResidentTiling const rt = resident_tiling(p, nsm);
     uint32_t const nTiles = uint32_t(rt.tiles.size());
     size_t const tile_blocks = rt.tile_blocks;
+    // Only really small systems: with more than 4 blocks per tile a CTA's four warps take several rounds over its Y blocks and
+    // the per-kernel path, which spreads the product over all SMs' threads, wins (measured on the block-size sweep, 1728 block
+    // rows: 4x5 fp32 with 20736 X blocks 10.6 vs 1.3 ms per solve, 4x32 with 3456 blocks 2.25 vs 1.79 ms; the FD example,
+    // 171 blocks: 1.06 vs 2.63 ms).  TFQMRGPU_RESIDENT_MAX_TILE overrides (dev).
+    {
+        char const *const e_mt = std::getenv("TFQMRGPU_RESIDENT_MAX_TILE");
+        size_t const max_tile = e_mt ? size_t(std::max(1, std::atoi(e_mt))) : 4;
+        if (tile_blocks > max_tile) return TFQ_ERR(TFQMRGPU_STATUS_LAUNCH_FAILED);
+    }
     int max_row = 1;                              // entries of a Y block <= blocks in its row of A
     for (int r = 0; r < p.mb; ++r) max_row = std::max(max_row, int(p.h_rpA[r + 1] - p.h_rpA[r]));
     int const max_e = std::min(max_row, 64);
@@ -707,8 +716,9 @@ tfqmrgpuStatus_t resident_dispatch(Plan &p, cudaStream_t stream, bool dry)
 
 } // namespace
 
-// Which plans run resident: blocks with LM <= 8 on the SIMT product, all vector tiles co-resident with their seven vectors in shared memory (vectors up to ~1.5 MB with 4 KiB tiles), no
-// user-defined operator, no shard exchange, no per-product profiling.  TFQMRGPU_RESIDENT=0 switches it off.
+// Which plans run resident: blocks with LM <= 8 (the SIMT product's sizes), at most 4 X blocks per SM (see launch_resident), all tiles
+// co-resident with their seven vectors in shared memory, no user-defined operator, no shard exchange, no per-product profiling.
+// TFQMRGPU_RESIDENT=0 switches it off.
 bool resident_supported(Plan &p)
 {
     // (read per solve: a getenv call is nothing next to a launch, and tests and callers can switch between solves)
@@ -717,7 +727,10 @@ bool resident_supported(Plan &p)
     if (p.use_tc16 || p.use_dmma || p.user_op || p.exch.slots || p.profile || p.multi) return false;
     if ('z' != p.precision && 'c' != p.precision) return false;
     if (p.LM > 8) return false;
-    return TFQMRGPU_STATUS_SUCCESS == resident_dispatch(p, nullptr, true);
+    // the structural part of the answer (tiling, shared memory, occupancy) is the same for every solve of a configured plan
+    if (p.resident_fits < 0 || std::getenv("TFQMRGPU_RESIDENT_MAX_TILE") || std::getenv("TFQMRGPU_RESIDENT_TILES_PER_SM"))
+        p.resident_fits = (TFQMRGPU_STATUS_SUCCESS == resident_dispatch(p, nullptr, true)) ? 1 : 0;
+    return 1 == p.resident_fits;
 }
 
 tfqmrgpuStatus_t launch_resident_solve(Plan &p, cudaStream_t stream, int /*maxIterations*/)

@@ -97,6 +97,7 @@ struct Plan {
     struct MultiPlan *multi = nullptr;       // in-process multi-GPU plan (multi.cu): this Plan is then only the global analysis
     int early_freeze = 0;                    // opt-in: freeze converged right-hand sides at the probes (tfqmrgpux_bsrsv_setEarlyFreeze)
     unsigned *d_resident_bar = nullptr;      // grid barrier of the resident solver (resident.cu)
+    int resident_fits = -1;                  // resident solver: does this configured plan qualify (-1: not yet asked)
     unsigned long long *d_resident_trace = nullptr;   // dev: time breakdown of the resident solver (TFQMRGPU_RESIDENT_TRACE)
     Tile *d_res_tiles = nullptr; uint32_t *d_res_coltile = nullptr; double *d_res_part = nullptr;   // resident solver: its own tiles
     uint32_t *d_unit_of_block = nullptr;     // resident solver: storage index of a Y block -> its unit (plans with gmax == 1)
