@@ -31,7 +31,7 @@ namespace tfq {
 
 namespace {
 
-constexpr int kResThreads = 128;
+constexpr int kResThreads = 256;
 constexpr int kResWarps = kResThreads/32;
 constexpr int kResLoads = 16;               // 128-bit loads in flight per lane while a batch of entries is staged
 
@@ -53,7 +53,7 @@ template <typename real_t> struct ResidentArgs {
     uint32_t tile_blocks;                     // blocks of the largest tile
     int eb;                                   // entries staged per batch and warp
     int max_e;                                // entries per Y block whose indices (and, a_resident, A blocks) are kept in shared memory
-    int warps_per_block;                      // warps that share one Y block in the product (1, 2 or 4)
+    int warps_per_block;                      // warps that share one Y block in the product (a power of two)
     int a_resident;                           // the A blocks of the tile's rows stay in shared memory for the whole solve
     int ablate;                               // dev: 1 = skip the FMAs of the product, 2 = skip its global loads
     unsigned long long *trace;                // dev: cycles of CTA 0 in [barriers, products, column sums, total, ...], or nullptr
@@ -632,7 +632,8 @@ tfqmrgpuStatus_t launch_resident(Plan &p, cudaStream_t stream, bool dry)
     int max_row = 1;                              // entries of a Y block <= blocks in its row of A
     for (int r = 0; r < p.mb; ++r) max_row = std::max(max_row, int(p.h_rpA[r + 1] - p.h_rpA[r]));
     int const max_e = std::min(max_row, 64);
-    int const W = (tile_blocks <= 1) ? 4 : ((tile_blocks <= 2) ? 2 : 1);
+    int W = 1;                                    // warps per Y block: as many as the CTA's warps allow for the largest tile
+    while (2*W <= kResWarps && size_t(2*W)*tile_blocks <= size_t(kResWarps)) W *= 2;
     // all tiles co-resident: k CTAs per SM, nsm*k >= nTiles; within that budget keep A in shared memory if it fits with at
     // least 4 staged entries per warp, and stage as many entries per batch as fit (at most a warp's share of a row)
     int const k = int((nTiles + nsm - 1)/nsm);
