@@ -103,6 +103,30 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_setRhsTrivial(tfqmrgpuHandle_t handle, tfqmrgpu
  * the next solve. */
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_setEarlyFreeze(tfqmrgpuBsrsvPlan_t plan, int on);
 
+/* ---- precision 'm' ("start with float and converge double", tfqmrgpu.h:72) ---------------------------------------------------
+ * The reference accepts 'm' in bufferSize (tfqmrgpu.cu:386) but its solver dispatch has the case commented out (tfqmrgpu.cu:42-44:
+ * solve returns PRECISION_MISSMATCH).  Here bufferSize(..., 'm', &bytes) configures an fp64-accurate solve whose iterations run in
+ * complex fp32 (on the tensor cores for 16/32/64 blocks): iterative refinement, R = B - A*X and X += D in fp64, A*D = R by the
+ * ordinary fp32 solver with every right-hand side scaled to unit size.  The caller passes DOUBLE data to setMatrix / getMatrix
+ * (precision argument 'z' or 'm'); the single workspace holds the fp64 side, the fp32 plan and the fp32 copy of the operator
+ * (made on the device by setMatrix('A')).  solve(threshold, maxIterations): threshold is met by the true fp64 residual of every
+ * right-hand side, maxIterations bounds the SUM of the fp32 iterations; getInfo reports that sum, the residual reached and the flops
+ * of both sides.  Status 9 (MAX_ITERATIONS) also when two passes in a row gain less than a factor of two.  Not combined with
+ * setDevices, setOperator or setMatrixPart.  TFQMRGPU_MIXED=0 restores the reference's refusal; TFQMRGPU_MIXED_INNER_TOL (default
+ * 1e-3), TFQMRGPU_MIXED_INNER_ITER (default max(40, maxIterations/4)) and TFQMRGPU_MIXED_FREEZE (default 1: the fp32 passes use the
+ * per-right-hand-side freeze of setEarlyFreeze) tune the passes.  Measured on one GPU's share of BASELINE config 4 (32^3 block rows,
+ * 32x32 blocks, 128 right-hand sides, sigma 1, tol 1e-9): 'z' 2125 ms (29 iterations), 'm' 736 ms (3 passes, 42 fp32 iterations),
+ * solutions equal to 2e-12 (tests/tools/bench_mixed.py, profiles/r02_bench_mixed.json).
+ *
+ * setInitialGuess (mixed plans only, after bufferSize): with on != 0 solve starts from the X uploaded with setMatrix('X') - or, on a
+ * second solve, from the previous solution - instead of zero.  (The reference zeroes X at the start of every solve, core.hxx:125,
+ * and so do the 'c' and 'z' plans of this library.)
+ * getMixedInfo: info[0] = 1 for a mixed plan, [1] refinement passes of the last solve, [2] fp32 iterations of the last solve,
+ * [3] bytes of the fp32 plan's window, [4] fp32 product: 0 SIMT, 1 tcgen05 direct form, 2 tcgen05 planar form, [5] 1 if the fp64
+ * product runs on DMMA. */
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setInitialGuess(tfqmrgpuBsrsvPlan_t plan, int on);
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getMixedInfo(tfqmrgpuBsrsvPlan_t plan, double info[8]);
+
 /* ---- several GPUs: the independent right-hand-side block columns of X/B are sharded, A is replicated --------
  *
  * (1) One process, several devices - for C, Fortran and Julia callers.  Call setDevices after createPlan and before

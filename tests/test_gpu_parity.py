@@ -912,3 +912,102 @@ def test_early_freeze_extension(resident, monkeypatch):
     assert set(np.unique(rhs)) <= {0, 2}
     if res["off"][0] == 0:      # both converged: the frozen solution is as good as the reference rule's to the threshold
         assert np.abs(X - res["off"][3]).max() <= 50*tol*np.abs(res["off"][3]).max()
+
+
+# ---- precision 'm' (mixed.cu): fp64 refinement around the fp32 solver; stubbed in the reference (tfqmrgpu.cu:42-44,386) --------------
+def _solve_plain(prob, prec, tol, maxit, guess=None, keep=False):
+    dt = np.float32 if prec == "c" else np.float64
+    vA = P.interleave(prob.A.val, dt); vB = P.interleave(prob.B.val, dt)
+    h, pl = _open(prob)
+    pl.buffer_size_for(prob.lm, prob.ln, prec); pl.set_buffer()
+    pl.set_matrix("A", vA, "n"); pl.set_matrix("B", vB, "n")
+    if guess is not None:
+        pl.set_initial_guess(True)
+        pl.set_matrix("X", guess, "n", L.LAYOUT_RRRRIIII)
+    st = pl.solve(tol, maxit)
+    out = dict(st=st, info=pl.info(), X=pl.get_matrix("X", "n", L.LAYOUT_RRRRIIII).reshape(pl.nnzbX, 2, prob.lm, prob.ln),
+               mixed=pl.mixed_info(), plan=pl.plan_info(), rhs_status=pl.rhs_status())
+    if keep:
+        out["pl"], out["h"] = pl, h
+    else:
+        pl.close(); h.close()
+    return out
+
+
+@pytest.mark.parametrize("lmln", [(4, 4), (8, 10), (16, 16), (16, 32), (32, 32), (32, 64), (64, 64)], ids=lambda v: f"{v[0]}x{v[1]}")
+def test_mixed_precision_reaches_the_fp64_solution(lmln):
+    """bufferSize(..., 'm'): double data in and out, iterations in fp32 (tensor cores for 16/32/64 blocks), true fp64 residual below
+    the threshold; X agrees with the plain fp64 solve within 10*tol*max|X| (the bar of the fp64 parity tests)."""
+    lm, ln = lmln
+    tol = 1e-10
+    prob = P.random_system(12, lm, ln, seed=lm*100 + ln, unsorted=True)
+    z = _solve_plain(prob, "z", tol, 200)
+    m = _solve_plain(prob, "m", tol, 200)
+    assert z["st"] == 0 and m["st"] == 0
+    assert m["plan"]["precision"] == ord("m") and z["plan"]["precision"] == ord("z")
+    assert m["mixed"]["mixed"] and m["mixed"]["passes"] >= 2 and not z["mixed"]["mixed"]
+    assert (m["mixed"]["inner_product"] == "simt") if lm < 16 else m["mixed"]["inner_product"].startswith("tcgen05")
+    assert m["info"]["residuum"] <= tol and m["info"]["iterations"] == m["mixed"]["inner_iterations"] > 0
+    assert m["info"]["flops"] > 0
+    assert m["X"].dtype == np.float64
+    assert _true_residual(prob, m["X"]) <= tol*1.01
+    assert np.abs(m["X"] - z["X"]).max() <= 10*tol*np.abs(z["X"]).max()
+
+
+def test_mixed_precision_initial_guess_second_solve_and_switch(monkeypatch):
+    lm, ln = 16, 16
+    prob = P.random_system(12, lm, ln, seed=77, unsorted=True)
+    rough = _solve_plain(prob, "m", 1e-5, 200)
+    assert rough["st"] == 0 and rough["info"]["residuum"] <= 1e-5
+    cold = _solve_plain(prob, "m", 1e-11, 200)
+    warm = _solve_plain(prob, "m", 1e-11, 200, guess=rough["X"], keep=True)
+    assert cold["st"] == 0 and warm["st"] == 0
+    assert warm["info"]["iterations"] < cold["info"]["iterations"]          # the guess saves the first pass(es)
+    assert _true_residual(prob, warm["X"]) <= 1.01e-11
+    assert np.abs(warm["X"] - cold["X"]).max() <= 1e-10*np.abs(cold["X"]).max()
+    pl, h = warm["pl"], warm["h"]
+    # a second solve on the same plan with the guess switch on continues from the solution: no iteration is needed
+    assert pl.solve(1e-11, 200) == 0 and pl.info()["iterations"] == 0 and pl.mixed_info()["passes"] == 0
+    # ... and with the switch off it starts from zero like the reference (core.hxx:125) and arrives at the same X
+    pl.set_initial_guess(False)
+    assert pl.solve(1e-11, 200) == 0 and pl.info()["iterations"] == cold["info"]["iterations"]
+    X2 = pl.get_matrix("X", "n", L.LAYOUT_RRRRIIII).reshape(cold["X"].shape)
+    assert np.array_equal(X2, cold["X"])                                     # bit-reproducible
+    # max iterations: the budget bounds the sum of the fp32 iterations
+    assert pl.solve(1e-11, 3) == L.STATUS_MAX_ITERATIONS and pl.info()["iterations"] == 3
+    # float data is refused by a mixed plan; a plain plan refuses the guess switch
+    v = np.zeros(prob.A.nnzb*2*lm*lm, np.float32)
+    assert L.decode_status(pl.set_matrix("A", v, "n", precision="c", check=False))[0] == L.PRECISION_MISSMATCH
+    pl.close(); h.close()
+    h, pl = _open(prob)
+    pl.buffer_size_for(lm, ln, "z"); pl.set_buffer()
+    assert L.decode_status(pl.set_initial_guess(True, check=False))[0] == L.NO_IMPLEMENTATION
+    # TFQMRGPU_MIXED=0: the reference's behaviour ('m' is refused)
+    monkeypatch.setenv("TFQMRGPU_MIXED", "0")
+    assert L.decode_status(-pl.buffer_size_for(lm, ln, "m", check=False))[0] == L.PRECISION_MISSMATCH
+    pl.close(); h.close()
+
+
+def test_mixed_precision_stencil_sigma1():
+    """The config-4 operator (27-point block stencil, sigma = 1, 32x32 blocks, tol 1e-9) on an 8^3 grid: 'm' against 'z'."""
+    import torch
+    from tfqmrgpu_b200 import synthetic
+    n, lm, ln, ncol, tol = 8, 32, 32, 4, 1e-9
+    sp = synthetic.Stencil27(n, lm, ln, ncol, sigma=1.0, dtype=np.float64, device="cuda")
+    res = {}
+    for prec in ("z", "m"):
+        h = api.Handle()
+        pl = api.BsrsvPlan(h, sp.mb, sp.rpA, sp.ciA, sp.rpX, sp.ciX, sp.rpB, sp.ciB)
+        pl.buffer_size_for(lm, ln, prec); pl.set_buffer()
+        pl.set_matrix("A", None, "n", raw_ptr=sp.valA_host.data_ptr())
+        pl.set_matrix("B", sp.valB)
+        st = pl.solve(tol, 200)
+        res[prec] = dict(st=st, info=pl.info(), X=pl.get_matrix("X", "n", L.LAYOUT_RRRRIIII), mixed=pl.mixed_info(), plan=pl.plan_info())
+        pl.close(); h.close()
+    z, m = res["z"], res["m"]
+    assert z["st"] == 0 and m["st"] == 0 and m["info"]["residuum"] <= tol
+    assert m["plan"]["use_dmma"] == 1 and m["mixed"]["inner_product"] == "tcgen05 planar" and m["mixed"]["dmma"]
+    assert 2 <= m["mixed"]["passes"] <= 6
+    assert np.abs(m["X"] - z["X"]).max() <= 10*tol*np.abs(z["X"]).max()
+    del sp
+    torch.cuda.empty_cache()

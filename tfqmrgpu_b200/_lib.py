@@ -35,7 +35,7 @@ EXT_SYMBOLS = [
     "tfqmrgpux_bsrsv_getWindow", "tfqmrgpux_bsrsv_getRhsStatus", "tfqmrgpux_bsrsv_getSolveStats", "tfqmrgpux_randomShadow",
     "tfqmrgpux_bsrsv_setProfiling", "tfqmrgpux_bsrsv_getSolveProfile", "tfqmrgpux_bsrsv_setOperator",
     "tfqmrgpux_bsrsv_setDevices", "tfqmrgpux_bsrsv_getDevices", "tfqmrgpux_bsrsv_setShardExchange",
-    "tfqmrgpux_bsrsv_setShardHints", "tfqmrgpux_bsrsv_getMatrixPartInfo", "tfqmrgpux_bsrsv_setMatrixPart", "tfqmrgpux_bsrsv_getTileBlocks", "tfqmrgpux_tileBlocksFor", "tfqmrgpux_bsrsv_setRhsTrivial", "tfqmrgpux_bsrsv_setEarlyFreeze",
+    "tfqmrgpux_bsrsv_setShardHints", "tfqmrgpux_bsrsv_getMatrixPartInfo", "tfqmrgpux_bsrsv_setMatrixPart", "tfqmrgpux_bsrsv_getTileBlocks", "tfqmrgpux_tileBlocksFor", "tfqmrgpux_bsrsv_setRhsTrivial", "tfqmrgpux_bsrsv_setEarlyFreeze", "tfqmrgpux_bsrsv_setInitialGuess", "tfqmrgpux_bsrsv_getMixedInfo",
 ]
 FORTRAN_SYMBOLS = [
     "tfqmrgpuprinterror_", "tfqmrgpucreatehandle_", "tfqmrgpudestroyhandle_", "tfqmrgpusetstream_",
@@ -131,6 +131,8 @@ def load():
     lib.tfqmrgpux_bsrsv_setMatrixPart.argtypes = [vp, vp, vp, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
     lib.tfqmrgpux_bsrsv_setRhsTrivial.restype = st; lib.tfqmrgpux_bsrsv_setRhsTrivial.argtypes = [vp, vp]
     lib.tfqmrgpux_bsrsv_setEarlyFreeze.restype = st; lib.tfqmrgpux_bsrsv_setEarlyFreeze.argtypes = [vp, C.c_int]
+    lib.tfqmrgpux_bsrsv_setInitialGuess.restype = st; lib.tfqmrgpux_bsrsv_setInitialGuess.argtypes = [vp, C.c_int]
+    lib.tfqmrgpux_bsrsv_getMixedInfo.restype = st; lib.tfqmrgpux_bsrsv_getMixedInfo.argtypes = [vp, C.POINTER(C.c_double)]
     lib.tfqmrgpux_tileBlocksFor.restype = st; lib.tfqmrgpux_tileBlocksFor.argtypes = [C.c_int64, C.c_int64, C.POINTER(C.c_int64)]
     _lib = lib
     return lib

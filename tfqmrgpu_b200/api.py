@@ -90,7 +90,8 @@ class BsrsvPlan:
         elif st:
             return -st
         self.lm, self.ln = lm, ln
-        self.precision = {"f": "c", "c": "c", "d": "z", "z": "z"}.get(precision.lower(), "z")
+        self.precision = {"f": "c", "c": "c", "d": "z", "z": "z"}.get(precision.lower(), "z")   # ('m' exchanges doubles)
+        self.mixed = precision.lower() == "m"
         self.buffer_size = size.value
         return size.value
 
@@ -286,6 +287,19 @@ class BsrsvPlan:
     def set_early_freeze(self, on=True):
         """Opt-in (not in the reference): a right-hand side whose true residual passes a probe keeps its X (status 2)."""
         _check(self.lib.tfqmrgpux_bsrsv_setEarlyFreeze(self.plan, int(bool(on))), "setEarlyFreeze")
+
+    def set_initial_guess(self, on=True, check=True):
+        """Mixed-precision plans ('m') only: start the solve from the uploaded X / the previous solution instead of zero."""
+        st = self.lib.tfqmrgpux_bsrsv_setInitialGuess(self.plan, int(bool(on)))
+        if check:
+            _check(st, "setInitialGuess")
+        return st
+
+    def mixed_info(self) -> dict:
+        v = (C.c_double*8)()
+        _check(self.lib.tfqmrgpux_bsrsv_getMixedInfo(self.plan, v), "getMixedInfo")
+        return dict(mixed=bool(v[0]), passes=int(v[1]), inner_iterations=int(v[2]), inner_bytes=int(v[3]),
+                    inner_product={0: "simt", 1: "tcgen05 direct", 2: "tcgen05 planar"}[int(v[4])], dmma=bool(v[5]))
 
     def set_rhs_trivial(self):
         """B := unit blocks (the reference's rhs_trivial right-hand sides) instead of set_matrix('B', ...)."""

@@ -34,10 +34,15 @@ void set_verbosity(int level) { g_verbosity.store(level < 0 ? 0 : level, std::me
 
 static inline Plan* P(tfqmrgpuBsrsvPlan_t plan) { return reinterpret_cast<Plan*>(plan); }
 static inline char lower(char c) { return char(c | 32); } // the reference's "| IgnoreCase" (util.hxx:12)
+// the precision argument of set/getMatrix: a mixed-precision plan ('m') exchanges doubles, under the name 'z' or 'm'
+static inline bool data_is_double(Plan const &p, char precision) {
+    char const c = lower(precision);
+    return ('z' == c) || (p.mixed && 'm' == c);
+}
 
 // random shadow vector: cuRAND XORWOW, seed 1234, generated in the caller's block order like the
 // reference (linalg.hxx:777-797), then moved into column-sorted storage order
-static tfqmrgpuStatus_t fill_v3(Plan &p, cudaStream_t stream) {
+tfqmrgpuStatus_t fill_v3(Plan &p, cudaStream_t stream) {
     size_t const n = size_t(p.nnzbX)*2*p.LM*p.LN;
     float *const scratch = ws<float>(p, p.off_v[9]);
     curandGenerator_t gen;
@@ -77,7 +82,7 @@ static tfqmrgpuStatus_t download_vector(Handle *h, Plan &p, size_t off_vec, void
     if (p.nnzbX < 1) return TFQMRGPU_STATUS_SUCCESS;
     if (nullptr == p.pBuffer || nullptr == val) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     bool const is_double = ('z' == p.precision);
-    if (('z' == lower(precision)) != is_double) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, precision);
+    if (data_is_double(p, precision) != is_double) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, precision);
     if (p.multi) {      // several devices: gather the shards' X device to device, convert on the home device
         if (off_vec != p.off_v[1]) return TFQ_ERR(TFQMRGPU_NO_IMPLEMENTATION);
         st = multi_gather_x(p, h->stream);
@@ -229,7 +234,17 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_bufferSize(tfqmrgpuHandle_t handle, tfqmrgpuBsrs
     if (nullptr == pBufferSizeInBytes) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     *pBufferSizeInBytes = 0;
     if (!block_size_allowed(LM, LN)) return TFQMRGPU_BLOCKSIZE_MISSING + TFQMRGPU_CODE_CHAR*LM + TFQMRGPU_CODE_LINE*LN; // tfqmrgpu.cu:70
-    if ('m' == prec) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, prec);                                             // tfqmrgpu.cu:44
+    if ('m' != prec) mixed_destroy(p);
+    if ('m' == prec) {
+        // The reference accepts 'm' here (tfqmrgpu.cu:386) and fails in solve (tfqmrgpu.cu:42-44: the case is commented out).
+        // This library implements it (mixed.cu); TFQMRGPU_MIXED=0 restores the reference's refusal.
+        char const *e = std::getenv("TFQMRGPU_MIXED");
+        if ((e && '0' == e[0]) || p.multi) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, prec);                      // tfqmrgpu.cu:44
+        tfqmrgpuStatus_t const xst = mixed_buffer_size(p, static_cast<Handle*>(handle)->stream, LM, LN, pBufferSizeInBytes);
+        if (TFQMRGPU_STATUS_SUCCESS != xst) { p.bufferBytes = 0; *pBufferSizeInBytes = 0; return xst; }
+        p.configured = true;
+        return TFQMRGPU_STATUS_SUCCESS;
+    }
     if (p.multi) {
         tfqmrgpuStatus_t const mst = multi_buffer_size(p, LM, LN, prec, pBufferSizeInBytes);
         if (TFQMRGPU_STATUS_SUCCESS != mst) { p.bufferBytes = 0; *pBufferSizeInBytes = 0; return mst; }
@@ -258,6 +273,7 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_setBuffer(tfqmrgpuHandle_t handle, tfqmrgpuBsrsv
     tfqmrgpuStatus_t const st = fill_v3(p, stream);
     if (TFQMRGPU_STATUS_SUCCESS != st) return st;
     p.v3_ready = true;
+    if (p.mixed) return mixed_set_buffer(p, stream);
     return TFQMRGPU_STATUS_SUCCESS;
 }
 tfqmrgpuStatus_t tfqmrgpu_bsrsv_getBuffer(tfqmrgpuHandle_t, tfqmrgpuBsrsvPlan_t plan, void* *pBuffer) {
@@ -331,10 +347,11 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_setMatrix(tfqmrgpuHandle_t handle, tfqmrgpuBsrsv
     if (nnzb < 1) return TFQMRGPU_STATUS_SUCCESS;
     if (nullptr == p.pBuffer || nullptr == val || !p.configured) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     if ('z' != p.precision && 'c' != p.precision) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, p.precision);
-    if (('z' == lower(precision)) != is_double) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, precision); // tfqmrgpu.cu:538-542
+    if (data_is_double(p, precision) != is_double) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, precision); // tfqmrgpu.cu:538-542
     if (p.multi) return multi_set_matrix(p, v, val, precision, transposition, layout, trans, scal_imag);
     if ('a' == v) {
         st = upload_a_blocks(p, stream, val, 0, nnzb, is_double, layout, trans, scal_imag);
+        if (TFQMRGPU_STATUS_SUCCESS == st && p.mixed) return mixed_after_set_a(p, stream);
         if (st || !p.use_tc16) return st;
         return launch_aop_convert(p, stream);
     }
@@ -369,6 +386,7 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_solve(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan
         if (nullptr == P(plan)->pBuffer || !P(plan)->configured) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
         return multi_solve(*P(plan), threshold, maxIterations);
     }
+    if (P(plan)->mixed) return mixed_solve(*P(plan), static_cast<Handle*>(handle)->stream, threshold, maxIterations);
     return solve(*P(plan), static_cast<Handle*>(handle)->stream, threshold, maxIterations);
 }
 
@@ -500,7 +518,7 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getPlanArray(tfqmrgpuBsrsvPlan_t plan, int kind
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_getPlanInfo(tfqmrgpuBsrsvPlan_t plan, int64_t info[16]) {
     if (nullptr == plan || nullptr == info) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     Plan const &p = *P(plan);
-    int64_t const v[16] = {p.nnzbX, p.nnzbB, p.nnzbA, int64_t(p.nCols), int64_t(p.nPairs), p.LM, p.LN, p.precision,
+    int64_t const v[16] = {p.nnzbX, p.nnzbB, p.nnzbA, int64_t(p.nCols), int64_t(p.nPairs), p.LM, p.LN, p.mixed ? int64_t('m') : int64_t(p.precision),
                            int64_t(p.nTiles), int64_t(p.nUnits), int64_t(p.gmax), int64_t(p.nEntries), p.mb, int64_t(p.use_tc16), int64_t(p.use_dmma), int64_t(p.use_small)};
     std::memcpy(info, v, sizeof(v));
     return TFQMRGPU_STATUS_SUCCESS;
@@ -603,7 +621,7 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getWindow(tfqmrgpuBsrsvPlan_t plan, char var, s
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_getRhsStatus(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, int8_t *statusHost) {
     if (nullptr == plan || nullptr == handle || nullptr == statusHost) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     if (P(plan)->multi) return (nullptr == P(plan)->pBuffer) ? TFQ_ERR(TFQMRGPU_POINTER_INVALID) : multi_rhs_status(*P(plan), statusHost);
-    Plan const &p = *P(plan);
+    Plan const &p = P(plan)->mixed ? *mixed_inner(*P(plan)) : *P(plan);     // (mixed precision: of the last fp32 pass)
     if (nullptr == p.pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     cudaStream_t const stream = static_cast<Handle*>(handle)->stream;
     // snap = the status array as the reference's host sees it after the last completed iteration / probe
@@ -687,6 +705,7 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_setMatrixPart(tfqmrgpuHandle_t handle, tfqmrgpu
     if (st) return st;
     if (nullptr == p.pBuffer) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     bool const is_double = ('z' == p.precision);
+    if (p.mixed) return TFQ_ERR(TFQMRGPU_NO_IMPLEMENTATION);
     if (('z' == lower(precision)) != is_double) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, precision);
     if (info[5] < 1) return TFQMRGPU_STATUS_SUCCESS;
     if (nullptr == valPart) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
@@ -708,6 +727,23 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_setEarlyFreeze(tfqmrgpuBsrsvPlan_t plan, int on
     Plan &p = *P(plan);
     p.early_freeze = on ? 1 : 0;
     if (p.multi) multi_set_early_freeze(p);
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setInitialGuess(tfqmrgpuBsrsvPlan_t plan, int on) {
+    if (nullptr == plan) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan &p = *P(plan);
+    if (nullptr == p.mixed) return on ? TFQ_ERR(TFQMRGPU_NO_IMPLEMENTATION) : TFQMRGPU_STATUS_SUCCESS;
+    mixed_use_guess(p, 0 != on);
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_getMixedInfo(tfqmrgpuBsrsvPlan_t plan, double info[8]) {
+    if (nullptr == plan || nullptr == info) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan const &p = *P(plan);
+    for (int i = 0; i < 8; ++i) info[i] = 0;
+    Plan const *const q = mixed_inner(p);
+    if (nullptr == q) return TFQMRGPU_STATUS_SUCCESS;
+    info[0] = 1; info[1] = mixed_passes(p); info[2] = p.iterations_run; info[3] = double(q->bufferBytes);
+    info[4] = q->use_tc16 ? (q->tc_planar ? 2 : 1) : 0; info[5] = p.use_dmma ? 1 : 0;
     return TFQMRGPU_STATUS_SUCCESS;
 }
 tfqmrgpuStatus_t tfqmrgpux_tileBlocksFor(int64_t nnzbX, int64_t blockBytes, int64_t *tileBlocks) {

@@ -376,6 +376,7 @@ static void free_configured(Plan &p) {
 
 void plan_release(Plan &p) {
     multi_destroy(p);
+    mixed_destroy(p);
     free_configured(p);
     cudaFree(p.d_starts); cudaFree(p.d_pairs); cudaFree(p.d_subset); cudaFree(p.d_colindx);
     cudaFree(p.d_perm); cudaFree(p.d_iperm); cudaFree(p.d_bpos); cudaFree(p.d_blockcol); cudaFree(p.d_rowptrA);

@@ -202,6 +202,7 @@ tfqmrgpuStatus_t solve_finish(Plan &p, Control const &fin, int bodies, double la
     p.flops_performed_all += p.flops_performed; // the reference never accumulates this (defect, fixed)
     p.residuum_reached = std::sqrt(fin.residual2_reached);
     p.iterations_needed = fin.iterations_needed;
+    p.iterations_run = fin.iteration;
     p.solved = true;
     p.stat_probes = fin.probes; p.stat_launches = launches; p.stat_bodies = bodies;
     p.stat_bound2 = fin.max_bound2; p.stat_target2 = fin.target_bound2;

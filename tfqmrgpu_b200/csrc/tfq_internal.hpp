@@ -95,6 +95,7 @@ struct Plan {
     bool use_dmma = false;            // complex fp64 product on the FP64 tensor pipe (spmm_dmma.cu)
     Exchange exch;
     struct MultiPlan *multi = nullptr;       // in-process multi-GPU plan (multi.cu): this Plan is then only the global analysis
+    struct MixedPlan *mixed = nullptr;       // precision 'm' (mixed.cu): this Plan is the fp64 side (precision == 'z') of a refinement around an fp32 plan
     int early_freeze = 0;                    // opt-in: freeze converged right-hand sides at the probes (tfqmrgpux_bsrsv_setEarlyFreeze)
     unsigned *d_resident_bar = nullptr;      // grid barrier of the resident solver (resident.cu)
     int resident_fits = -1;                  // resident solver: does this configured plan qualify (-1: not yet asked)
@@ -147,6 +148,7 @@ struct Plan {
     // ---- stats (tfqmrgpu_plan.hxx:41-45) -------------------------------------------------------
     double residuum_reached = 0, flops_performed = -1, flops_performed_all = 0;
     int    iterations_needed = -1;
+    int    iterations_run = 0;        // iterations the last solve really ran (iterations_needed keeps the reference's meaning)
     double stat_probes = 0, stat_launches = 0, stat_bodies = 0, stat_ms = 0, stat_bound2 = 0, stat_target2 = 0;
     // optional device-side profile of the last solve (tfqmrgpux_bsrsv_setProfiling)
     bool   profile = false;
@@ -179,6 +181,17 @@ size_t multi_off_gx(Plan const &p);
 size_t multi_off_scratch(Plan const &p);
 tfqmrgpuStatus_t multi_rhs_status(Plan &p, int8_t *statusHost);
 void multi_set_early_freeze(Plan &p);
+
+// ---- precision 'm': fp64 refinement around the fp32 solver (mixed.cu) -------------------------------------
+tfqmrgpuStatus_t mixed_buffer_size(Plan &p, cudaStream_t stream, int LM, int LN, size_t *bytes);
+tfqmrgpuStatus_t mixed_set_buffer(Plan &p, cudaStream_t stream);      // after the fp64 side has been attached
+tfqmrgpuStatus_t mixed_after_set_a(Plan &p, cudaStream_t stream);     // fp32 operand from the uploaded fp64 operator
+tfqmrgpuStatus_t mixed_solve(Plan &p, cudaStream_t stream, double tolerance, int maxIterations);
+void  mixed_destroy(Plan &p);
+Plan* mixed_inner(Plan const &p);
+int   mixed_passes(Plan const &p);
+void  mixed_use_guess(Plan &p, bool on);
+tfqmrgpuStatus_t fill_v3(Plan &p, cudaStream_t stream);               // api.cu: the reference's cuRAND shadow vector
 
 // ---- kernels' host launchers --------------------------------------------------------------------
 // block-sparse product y = A*x on storage-ordered vectors; gate: run only if ctl->state == expect (expect < 0: always)
