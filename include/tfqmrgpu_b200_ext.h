@@ -118,9 +118,11 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_setEarlyFreeze(tfqmrgpuBsrsvPlan_t plan, int on
  * 32x32 blocks, 128 right-hand sides, sigma 1, tol 1e-9): 'z' 2125 ms (29 iterations), 'm' 736 ms (3 passes, 42 fp32 iterations),
  * solutions equal to 2e-12 (tests/tools/bench_mixed.py, profiles/r02_bench_mixed.json).
  *
- * setInitialGuess (mixed plans only, after bufferSize): with on != 0 solve starts from the X uploaded with setMatrix('X') - or, on a
- * second solve, from the previous solution - instead of zero.  (The reference zeroes X at the start of every solve, core.hxx:125,
- * and so do the 'c' and 'z' plans of this library.)
+ * setInitialGuess (every single-device plan): with on != 0 solve starts from the X uploaded with setMatrix('X') - or, on a second
+ * solve, from the previous solution - instead of zero.  (The reference zeroes X at the start of every solve, core.hxx:125, and so
+ * does this library by default.)  'c' / 'z' plans run tfQMR on r0 = b - A*x0: one extra product before the first iteration, v1
+ * accumulates the corrections on top of x0, the residual probe and the convergence bound stay relative to |b|; small systems then
+ * take the per-kernel path instead of the resident solver.  Mixed plans start their refinement from X.
  * getMixedInfo: info[0] = 1 for a mixed plan, [1] refinement passes of the last solve, [2] fp32 iterations of the last solve,
  * [3] bytes of the fp32 plan's window, [4] fp32 product: 0 SIMT, 1 tcgen05 direct form, 2 tcgen05 planar form, [5] 1 if the fp64
  * product runs on DMMA. */

@@ -975,13 +975,12 @@ def test_mixed_precision_initial_guess_second_solve_and_switch(monkeypatch):
     assert np.array_equal(X2, cold["X"])                                     # bit-reproducible
     # max iterations: the budget bounds the sum of the fp32 iterations
     assert pl.solve(1e-11, 3) == L.STATUS_MAX_ITERATIONS and pl.info()["iterations"] == 3
-    # float data is refused by a mixed plan; a plain plan refuses the guess switch
+    # float data is refused by a mixed plan
     v = np.zeros(prob.A.nnzb*2*lm*lm, np.float32)
     assert L.decode_status(pl.set_matrix("A", v, "n", precision="c", check=False))[0] == L.PRECISION_MISSMATCH
     pl.close(); h.close()
     h, pl = _open(prob)
     pl.buffer_size_for(lm, ln, "z"); pl.set_buffer()
-    assert L.decode_status(pl.set_initial_guess(True, check=False))[0] == L.NO_IMPLEMENTATION
     # TFQMRGPU_MIXED=0: the reference's behaviour ('m' is refused)
     monkeypatch.setenv("TFQMRGPU_MIXED", "0")
     assert L.decode_status(-pl.buffer_size_for(lm, ln, "m", check=False))[0] == L.PRECISION_MISSMATCH
@@ -1011,3 +1010,22 @@ def test_mixed_precision_stencil_sigma1():
     assert np.abs(m["X"] - z["X"]).max() <= 10*tol*np.abs(z["X"]).max()
     del sp
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("lmln,prec,tol,rough_tol", [((4, 4), "z", 1e-9, 1e-4), ((8, 8), "z", 1e-9, 1e-4), ((32, 32), "z", 1e-9, 1e-4),
+                                                   ((16, 16), "z", 1e-9, 1e-4), ((8, 10), "c", 1e-4, 1e-2), ((16, 32), "c", 1e-4, 1e-2),
+                                                   ((32, 32), "c", 1e-4, 1e-2)],
+                         ids=lambda v: f"{v[0]}x{v[1]}" if isinstance(v, tuple) else str(v))
+def test_initial_guess_extension(lmln, prec, tol, rough_tol):
+    """tfqmrgpux_bsrsv_setInitialGuess (the reference zeroes X, core.hxx:125): tfQMR on r0 = b - A*x0.  A solve that
+    starts from a rough solution needs fewer iterations than the cold one and arrives at the same X; the bound stays relative to |b|."""
+    lm, ln = lmln
+    prob = P.random_system(12, lm, ln, seed=lm*100 + ln + 7, unsorted=True)
+    cold = _solve_plain(prob, prec, tol, 200)
+    rough = _solve_plain(prob, prec, rough_tol, 200)
+    warm = _solve_plain(prob, prec, tol, 200, guess=rough["X"])
+    assert cold["st"] == 0 and rough["st"] == 0 and warm["st"] == 0
+    assert 0 < warm["info"]["iterations"] < cold["info"]["iterations"]
+    assert warm["info"]["residuum"] <= tol
+    assert _true_residual(prob, warm["X"].astype(np.float64)) <= (tol*1.01 if prec == "z" else 5*tol)
+    assert np.abs(warm["X"] - cold["X"]).max() <= (10 if prec == "z" else 50)*tol*np.abs(cold["X"]).max()

@@ -360,7 +360,7 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_setMatrix(tfqmrgpuHandle_t handle, tfqmrgpuBsrsv
         TFQ_CUDA(cudaMemcpyAsync(dst, val, size_t(nnzb)*2*p.LM*p.LN*s, cudaMemcpyHostToDevice, stream));
         return convert_inplace(p, dst, nnzb, p.LM, p.LN, is_double, layout, trans, scal_imag, stream);
     }
-    // 'x': accepted like in the reference; note that solve() discards the initial guess (core.hxx:125)
+    // 'x': accepted like in the reference; solve() discards the initial guess (core.hxx:125) unless tfqmrgpux_bsrsv_setInitialGuess is on
     char *const scratch = p.pBuffer + p.off_v[9];
     TFQ_CUDA(cudaMemcpyAsync(scratch, val, p.vecBytes, cudaMemcpyHostToDevice, stream));
     st = convert_permuted(p, p.pBuffer + p.off_v[1], scratch, nnzb, p.LM, p.LN, is_double, layout, trans, scal_imag, true, stream);
@@ -732,8 +732,8 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_setEarlyFreeze(tfqmrgpuBsrsvPlan_t plan, int on
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_setInitialGuess(tfqmrgpuBsrsvPlan_t plan, int on) {
     if (nullptr == plan) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     Plan &p = *P(plan);
-    if (nullptr == p.mixed) return on ? TFQ_ERR(TFQMRGPU_NO_IMPLEMENTATION) : TFQMRGPU_STATUS_SUCCESS;
-    mixed_use_guess(p, 0 != on);
+    if (p.multi) return on ? TFQ_ERR(TFQMRGPU_NO_IMPLEMENTATION) : TFQMRGPU_STATUS_SUCCESS;
+    p.initial_guess = on ? 1 : 0;
     return TFQMRGPU_STATUS_SUCCESS;
 }
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_getMixedInfo(tfqmrgpuBsrsvPlan_t plan, double info[8]) {

@@ -32,7 +32,6 @@ struct MixedPlan {
     double *h_rn2 = nullptr;           // pinned: column norms read back per pass
     uint32_t *d_colstart = nullptr;    // [nCols+1] first storage block of every block column
     std::vector<double> bn2;           // |b|^2 per right-hand side
-    bool   use_guess = false;
     bool   a_ready = false;
     int    passes = 0;
 };
@@ -137,12 +136,10 @@ void mixed_destroy(Plan &p)
 
 Plan* mixed_inner(Plan const &p) { return p.mixed ? p.mixed->inner : nullptr; }
 int   mixed_passes(Plan const &p) { return p.mixed ? p.mixed->passes : 0; }
-void  mixed_use_guess(Plan &p, bool on) { if (p.mixed) p.mixed->use_guess = on; }
 
 // bufferSize(..., 'm'): the fp64 plan, the fp32 plan and the scratch of the refinement in ONE caller-owned workspace
 tfqmrgpuStatus_t mixed_buffer_size(Plan &p, cudaStream_t stream, int LM, int LN, size_t *bytes)
 {
-    bool const keep_guess = p.mixed ? p.mixed->use_guess : false;
     tfqmrgpuStatus_t st = plan_configure(p, stream, LM, LN, 'z');
     if (TFQMRGPU_STATUS_SUCCESS != st) return st;
     if (nullptr == p.mixed) {
@@ -150,7 +147,7 @@ tfqmrgpuStatus_t mixed_buffer_size(Plan &p, cudaStream_t stream, int LM, int LN,
         if (nullptr == p.mixed) return TFQ_ERR(TFQMRGPU_STATUS_ALLOCATION_FAILED);
     }
     MixedPlan &m = *p.mixed;
-    m.use_guess = keep_guess; m.a_ready = false;
+    m.a_ready = false;
     if (nullptr == m.inner) {
         m.inner = new (std::nothrow) Plan();
         if (nullptr == m.inner) { mixed_destroy(p); return TFQ_ERR(TFQMRGPU_STATUS_ALLOCATION_FAILED); }
@@ -275,7 +272,7 @@ tfqmrgpuStatus_t mixed_solve(Plan &p, cudaStream_t stream, double tolerance, int
     // pass then runs into its iteration cap (config-4 shard, 128 right-hand sides: 75 instead of 42 fp32 iterations, 1282 vs 736 ms);
     // the fp64 residual of the next pass checks every column anyway.  TFQMRGPU_MIXED_FREEZE=0 switches it off.
     { char const *e = std::getenv("TFQMRGPU_MIXED_FREEZE"); q.early_freeze = (e && '0' == e[0]) ? 0 : 1; }
-    if (!m.use_guess) TFQ_CUDA(cudaMemsetAsync(X, 0, p.vecBytes, stream));       // like the reference (core.hxx:125)
+    if (!p.initial_guess) TFQ_CUDA(cudaMemsetAsync(X, 0, p.vecBytes, stream));       // like the reference (core.hxx:125)
 
     // |b|^2 per right-hand side
     TFQ_CUDA(cudaMemsetAsync(Y, 0, p.vecBytes, stream));
@@ -288,7 +285,7 @@ tfqmrgpuStatus_t mixed_solve(Plan &p, cudaStream_t stream, double tolerance, int
     tfqmrgpuStatus_t result = TFQMRGPU_STATUS_MAX_ITERATIONS;
     for (int pass = 0; ; ++pass) {
         // ---- R = B - A*X in fp64 (kept with the opposite sign in Y) and its column norms --------------------------------------
-        if (0 == pass && !m.use_guess) {
+        if (0 == pass && !p.initial_guess) {
             TFQ_CUDA(cudaMemsetAsync(Y, 0, p.vecBytes, stream));
         } else {
             TFQ_DO(launch_spmm(p, Y, X, -1, stream));

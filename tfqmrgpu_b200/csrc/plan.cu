@@ -359,6 +359,7 @@ void plan_drop_graph(Plan &p) {
 
 static void free_configured(Plan &p) {
     plan_drop_graph(p);
+    cudaFree(p.d_guess_scratch); p.d_guess_scratch = nullptr;
     cudaFree(p.d_tiles); p.d_tiles = nullptr;
     cudaFree(p.d_coltile); p.d_coltile = nullptr;
     cudaFree(p.d_unit_e0); p.d_unit_e0 = nullptr;
@@ -380,6 +381,7 @@ void plan_release(Plan &p) {
     free_configured(p);
     cudaFree(p.d_starts); cudaFree(p.d_pairs); cudaFree(p.d_subset); cudaFree(p.d_colindx);
     cudaFree(p.d_perm); cudaFree(p.d_iperm); cudaFree(p.d_bpos); cudaFree(p.d_blockcol); cudaFree(p.d_rowptrA);
+    if (p.d_guess_scratch) cudaFree(p.d_guess_scratch);
     if (p.d_resident_bar) cudaFree(p.d_resident_bar);
     if (p.d_resident_trace) cudaFree(p.d_resident_trace);
     if (p.h_ctl) cudaFreeHost(p.h_ctl);

@@ -9,6 +9,7 @@
 // at an asynchronous read-back of the control block a few bodies behind, so host and device never
 // serialise inside the loop while the iteration/probe sequence stays exactly the reference's.
 #include "tfq_internal.hpp"
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -48,6 +49,11 @@ struct TfqRange {
 
 namespace {
 __global__ void set_control_kernel(Control *ctl, Control const init) { *ctl = init; }
+// r := r - y  (initial guess: v5 = b - A*x0)
+template <typename real_t>
+__global__ void subtract_kernel(real_t *__restrict__ r, real_t const *__restrict__ y, size_t n) {
+    for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x)*blockDim.x) r[i] -= y[i];
+}
 }
 
 namespace {
@@ -181,8 +187,10 @@ tfqmrgpuStatus_t solve_begin(Plan &p, cudaStream_t stream, double tolerance, int
     set_control_kernel<<<1, 1, 0, stream>>>(d_ctl, c0);
     TFQ_CUDA(cudaGetLastError());
     TFQ_CUDA(cudaMemsetAsync(p.pBuffer + p.off_ticket, 0, (size_t(p.nCols) + 8)*4, stream));
-    // v1 and v4..v9 are contiguous: the initial guess is discarded like in the reference (core.hxx:125)
-    TFQ_CUDA(cudaMemsetAsync(p.pBuffer + p.off_v[1], 0, (p.off_v[9] + p.vecBytes) - p.off_v[1], stream));
+    // v1 and v4..v9 are contiguous: the initial guess is discarded like in the reference (core.hxx:125) unless the caller asked
+    // for it (tfqmrgpux_bsrsv_setInitialGuess: v1 keeps what setMatrix('X') uploaded / the previous solve left)
+    size_t const first = p.initial_guess ? p.off_v[4] : p.off_v[1];
+    TFQ_CUDA(cudaMemsetAsync(p.pBuffer + first, 0, (p.off_v[9] + p.vecBytes) - first, stream));
     if (p.use_tc16) TFQ_CUDA(cudaMemsetAsync(p.pBuffer + p.off_mx, 0, 3*size_t(p.nCols)*p.LN*sizeof(float), stream));   // max|v6| = 0
     p.exch.parity = 0;
     p.xop_of_x = false;             // the iterations overwrite the tensor-core operand (and X itself)
@@ -190,7 +198,30 @@ tfqmrgpuStatus_t solve_begin(Plan &p, cudaStream_t stream, double tolerance, int
     tfqmrgpuStatus_t st;
     st = launch_add_rhs(p, p.pBuffer + p.off_v[5], 1.0, -1, stream);       // v5 := b        (core.hxx:153)
     if (TFQMRGPU_STATUS_SUCCESS != st) return st;
-    return launch_vecop(p, OP_INIT, stream);                               // tau, 1/|b|^2, first dec35
+    st = launch_vecop(p, OP_INIT, stream);                                 // tau, 1/|b|^2, first dec35
+    p.guess_flops = 0;
+    if (TFQMRGPU_STATUS_SUCCESS != st || !p.initial_guess) return st;
+
+    // ---- initial guess x0 = v1 (not in the reference, which zeroes X: core.hxx:125): tfQMR on the residual r0 = b - A*x0.  The
+    //      iteration is unchanged - v1 accumulates the corrections on top of x0, the probe evaluates A*v1 - b - only its start
+    //      differs: v5 = r0, tau = |r0|^2 and the first rho = v3.r0, while the convergence bound stays relative to |b|
+    //      (1/|b|^2 from the first INIT is kept).
+    size_t const nrhs = size_t(p.nCols)*p.LN;
+    if (nullptr == p.d_guess_scratch) TFQ_CUDA(cudaMalloc((void**)&p.d_guess_scratch, nrhs*sizeof(double)));
+    TFQ_CUDA(cudaMemcpyAsync(p.d_guess_scratch, p.pBuffer + p.off_invBn2, nrhs*sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    st = launch_spmm(p, p.pBuffer + p.off_v[9], p.pBuffer + p.off_v[1], -1, stream);
+    if (TFQMRGPU_STATUS_SUCCESS != st) return st;
+    size_t const n = size_t(p.nnzbX)*2*p.LM*p.LN;
+    int const grid = int(std::min<size_t>((n + 255)/256, size_t(148)*16));
+    if ('z' == p.precision) subtract_kernel<double><<<grid, 256, 0, stream>>>(ws<double>(p, p.off_v[5]), ws<double const>(p, p.off_v[9]), n);
+    else                    subtract_kernel<float ><<<grid, 256, 0, stream>>>(ws<float >(p, p.off_v[5]), ws<float const >(p, p.off_v[9]), n);
+    TFQ_CUDA(cudaGetLastError());
+    TFQ_CUDA(cudaMemsetAsync(p.pBuffer + p.off_v[9], 0, p.vecBytes, stream));
+    st = launch_vecop(p, OP_INIT, stream);                                 // tau = |r0|^2, first dec35 on r0
+    if (TFQMRGPU_STATUS_SUCCESS != st) return st;
+    TFQ_CUDA(cudaMemcpyAsync(p.pBuffer + p.off_invBn2, p.d_guess_scratch, nrhs*sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    p.guess_flops = double(p.nPairs)*8.*p.LM*p.LM*p.LN + 2.*double(n);
+    return TFQMRGPU_STATUS_SUCCESS;
 }
 
 tfqmrgpuStatus_t solve_finish(Plan &p, Control const &fin, int bodies, double launches)
@@ -198,7 +229,7 @@ tfqmrgpuStatus_t solve_finish(Plan &p, Control const &fin, int bodies, double la
     // ---- bookkeeping (core.hxx:133-138,324-325; flop formula of SURVEY.md a14) ------------------------
     double const N = double(p.nnzbX)*p.LM*p.LN;
     double const M = double(p.nPairs)*8.*p.LM*p.LM*p.LN;
-    p.flops_performed = fin.iteration*(104.*N + 2.*M) + 4.*N + fin.probes*(M + 4.*N);
+    p.flops_performed = fin.iteration*(104.*N + 2.*M) + 4.*N + fin.probes*(M + 4.*N) + p.guess_flops;
     p.flops_performed_all += p.flops_performed; // the reference never accumulates this (defect, fixed)
     p.residuum_reached = std::sqrt(fin.residual2_reached);
     p.iterations_needed = fin.iterations_needed;
@@ -227,7 +258,7 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
     TFQ_CUDA(mark(0));
     // (a callback cannot be captured blindly; the exchange hook of a sharded run is a host call per iteration)
     bool const use_graph = graphs_enabled() && !p.profile && maxIterations > 0 && nullptr == p.user_op && nullptr == p.exch.slots
-                           && !resident_supported(p);
+                           && !(resident_supported(p) && !p.initial_guess);
     if (use_graph && nullptr == p.body_exec) {
         tfqmrgpuStatus_t const gst = build_body_graph(p);
         if (TFQMRGPU_STATUS_SUCCESS != gst) return gst;
@@ -246,7 +277,7 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
 
     int bodies = 0;
     // small systems: the whole solve in one cooperative launch (resident.cu); the loop below is skipped
-    bool const resident = maxIterations > 0 && resident_supported(p);
+    bool const resident = maxIterations > 0 && !p.initial_guess && resident_supported(p);   // (the resident solver starts from X = 0)
     if (resident) {
         st = launch_resident_solve(p, stream, maxIterations);
         if (TFQMRGPU_STATUS_SUCCESS != st) return st;

@@ -96,6 +96,8 @@ struct Plan {
     Exchange exch;
     struct MultiPlan *multi = nullptr;       // in-process multi-GPU plan (multi.cu): this Plan is then only the global analysis
     struct MixedPlan *mixed = nullptr;       // precision 'm' (mixed.cu): this Plan is the fp64 side (precision == 'z') of a refinement around an fp32 plan
+    int initial_guess = 0;                  // opt-in: solve starts from v1 instead of zero (tfqmrgpux_bsrsv_setInitialGuess)
+    double *d_guess_scratch = nullptr; double guess_flops = 0;
     int early_freeze = 0;                    // opt-in: freeze converged right-hand sides at the probes (tfqmrgpux_bsrsv_setEarlyFreeze)
     unsigned *d_resident_bar = nullptr;      // grid barrier of the resident solver (resident.cu)
     int resident_fits = -1;                  // resident solver: does this configured plan qualify (-1: not yet asked)
@@ -190,7 +192,6 @@ tfqmrgpuStatus_t mixed_solve(Plan &p, cudaStream_t stream, double tolerance, int
 void  mixed_destroy(Plan &p);
 Plan* mixed_inner(Plan const &p);
 int   mixed_passes(Plan const &p);
-void  mixed_use_guess(Plan &p, bool on);
 tfqmrgpuStatus_t fill_v3(Plan &p, cudaStream_t stream);               // api.cu: the reference's cuRAND shadow vector
 
 // ---- kernels' host launchers --------------------------------------------------------------------
