@@ -90,6 +90,14 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_getSolveProfile(tfqmrgpuBsrsvPlan_t plan, doubl
 typedef int32_t (*tfqmrgpuxOperator_t)(void *ctx, void *y, void const *x, int32_t const *state, int32_t expect, cudaStream_t stream);
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_setOperator(tfqmrgpuBsrsvPlan_t plan, tfqmrgpuxOperator_t op, void *ctx);
 
+/* Right preconditioner - the slot the reference left commented out (tfqmrgpu_core.hxx:37,57: `action.has_preconditioner()`, `vP`).
+ * `op` has the signature and the rules of a user-defined operator and computes z = P*x for X-shaped vectors in the solver's storage,
+ * P being an approximate inverse of A that acts within every right-hand-side column.  With a preconditioner set, solve() runs tfQMR
+ * on A*P (every product becomes A*(P*v) through one extra vector owned by the plan; the residual probe evaluates A*(P*v1) - b, so
+ * threshold and residual keep their meaning) and returns X = P*v1.  Kernel-by-kernel launches (no CUDA graph, no resident solver);
+ * not combined with setInitialGuess, setDevices or precision 'm'.  `op` = NULL removes it. */
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setPreconditioner(tfqmrgpuBsrsvPlan_t plan, tfqmrgpuxOperator_t op, void *ctx);
+
 /* The right-hand sides of the reference's `rhs_trivial` mode (tfqmrgpu_core.hxx:27,140-147: "columns of the unit matrix"): every
  * B block becomes the unit block (Re b[j mod LM][j] = 1).  Instead of setMatrix('B'); the reference offers this only to C++ callers
  * of its solve() template. */

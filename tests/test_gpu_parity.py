@@ -25,8 +25,8 @@ CASES = golden_cases()
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _open(prob, index_offset=0):
-    h = api.Handle()
+def _open(prob, index_offset=0, stream=0):
+    h = api.Handle(stream)
     o = index_offset
     pl = api.BsrsvPlan(h, prob.mb, prob.A.rowptr + o, prob.A.colind + o, prob.X.rowptr + o, prob.X.colind + o,
                        prob.B.rowptr + o, prob.B.colind + o, index_offset=o)
@@ -558,7 +558,8 @@ def test_user_defined_operator_matches_builtin_product(prec):
     base = _solve_case(prob, prec, tol, 200, "n", "n")
     dt, ts, tdt = (np.float64, "<f8", torch.float64) if prec == "z" else (np.float32, "<f4", torch.float32)
     vA = P.interleave(prob.A.val, dt); vB = P.interleave(prob.B.val, dt)
-    h, pl = _open(prob)
+    side = torch.cuda.Stream()          # (see test_right_preconditioner_slot: no torch work through ExternalStream(0))
+    h, pl = _open(prob, stream=side.cuda_stream)
     pl.buffer_size_for(lm, ln, prec); pl.set_buffer()
     lists = pl.plan_lists()
     perm = torch.as_tensor(lists["perm"].astype(np.int64), device="cuda")
@@ -569,6 +570,7 @@ def test_user_defined_operator_matches_builtin_product(prec):
     sy = perm[torch.as_tensor(ydst, device="cuda")]                    # storage index of every pair's Y block
     Ac = torch.as_tensor(prob.A.val.astype(np.complex128 if prec == "z" else np.complex64), device="cuda")   # [nnzbA][i][k], 'n'
     shape = (pl.nnzbX, 2, lm, ln)
+    torch.cuda.synchronize()
     calls = []
 
     def op(y_ptr, x_ptr, state_ptr, expect, stream):
@@ -1029,3 +1031,54 @@ def test_initial_guess_extension(lmln, prec, tol, rough_tol):
     assert warm["info"]["residuum"] <= tol
     assert _true_residual(prob, warm["X"].astype(np.float64)) <= (tol*1.01 if prec == "z" else 5*tol)
     assert np.abs(warm["X"] - cold["X"]).max() <= (10 if prec == "z" else 50)*tol*np.abs(cold["X"]).max()
+
+
+@pytest.mark.parametrize("lmln,prec", [((8, 8), "z"), ((32, 32), "z"), ((32, 32), "c"), ((4, 5), "c")], ids=lambda v: f"{v[0]}x{v[1]}" if isinstance(v, tuple) else v)
+def test_right_preconditioner_slot(lmln, prec):
+    """tfqmrgpux_bsrsv_setPreconditioner (the slot the reference left commented out, core.hxx:37,57): tfQMR on A*P with X = P*y.  Here P is a
+    positive diagonal scaling that differs per element (so A*P is a different operator in every right-hand-side column): the solve must
+    arrive at the solution of the unpreconditioned system, with the true residual below the threshold."""
+    import torch
+    lm, ln = lmln
+    tol = 1e-9 if prec == "z" else 1e-4
+    prob = P.random_system(12, lm, ln, seed=lm*10 + ln, unsorted=True)
+    base = _solve_plain(prob, prec, tol, 200)
+    dt, ts, tdt = (np.float64, "<f8", torch.float64) if prec == "z" else (np.float32, "<f4", torch.float32)
+    vA = P.interleave(prob.A.val, dt); vB = P.interleave(prob.B.val, dt)
+    # the handle gets a torch stream of its own: torch work queued through ExternalStream(0) is NOT ordered with the library's kernels on
+    # the legacy default stream (tests/tools/dev_precond_diag.py: identity by cudaMemcpyAsync or on a side stream is exact, through
+    # ExternalStream(0) it is not)
+    side = torch.cuda.Stream()
+    h, pl = _open(prob, stream=side.cuda_stream)
+    pl.buffer_size_for(lm, ln, prec); pl.set_buffer()
+    shape = (pl.nnzbX, 2, lm, ln)
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    d = (0.5 + torch.rand((pl.nnzbX, 1, lm, ln), generator=g, device="cuda", dtype=tdt))      # the same factor for Re and Im
+    torch.cuda.synchronize()
+    calls = []
+
+    def pc(z_ptr, x_ptr, state_ptr, expect, stream):
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+            x = torch.as_tensor(_DevArray(x_ptr, shape, ts), device="cuda")
+            z = torch.as_tensor(_DevArray(z_ptr, shape, ts), device="cuda")
+            torch.mul(x, d, out=z)
+        calls.append(expect)
+        return 0
+    pl.set_preconditioner(pc)
+    pl.set_matrix("A", vA, "n"); pl.set_matrix("B", vB, "n")
+    st = pl.solve(tol, 200)
+    info = pl.info()
+    X = pl.get_matrix("X", "n", L.LAYOUT_RRRRIIII).reshape(shape)
+    assert st == 0 and info["residuum"] <= tol
+    assert len(calls) >= 2*info["iterations"] + 2 and calls[-1] == -1      # the products, the probes, and X = P*v1 at the end
+    assert _true_residual(prob, X.astype(np.float64)) <= (tol*1.01 if prec == "z" else 5*tol)
+    assert np.abs(X - base["X"]).max() <= (10 if prec == "z" else 50)*tol*np.abs(base["X"]).max()
+    # without it, the same plan reproduces the plain solve bit for bit
+    pl.set_preconditioner(None)
+    assert pl.solve(tol, 200) == 0 and pl.info()["iterations"] == base["info"]["iterations"]
+    assert np.array_equal(pl.get_matrix("X", "n", L.LAYOUT_RRRRIIII).reshape(shape), base["X"])
+    # not with an initial guess
+    pl.set_preconditioner(pc); pl.set_initial_guess(True)
+    with pytest.raises(api.TfqmrError):
+        pl.solve(tol, 200)
+    pl.close(); h.close()

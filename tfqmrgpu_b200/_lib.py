@@ -35,7 +35,7 @@ EXT_SYMBOLS = [
     "tfqmrgpux_bsrsv_getWindow", "tfqmrgpux_bsrsv_getRhsStatus", "tfqmrgpux_bsrsv_getSolveStats", "tfqmrgpux_randomShadow",
     "tfqmrgpux_bsrsv_setProfiling", "tfqmrgpux_bsrsv_getSolveProfile", "tfqmrgpux_bsrsv_setOperator",
     "tfqmrgpux_bsrsv_setDevices", "tfqmrgpux_bsrsv_getDevices", "tfqmrgpux_bsrsv_setShardExchange",
-    "tfqmrgpux_bsrsv_setShardHints", "tfqmrgpux_bsrsv_getMatrixPartInfo", "tfqmrgpux_bsrsv_setMatrixPart", "tfqmrgpux_bsrsv_getTileBlocks", "tfqmrgpux_tileBlocksFor", "tfqmrgpux_bsrsv_setRhsTrivial", "tfqmrgpux_bsrsv_setEarlyFreeze", "tfqmrgpux_bsrsv_setInitialGuess", "tfqmrgpux_bsrsv_getMixedInfo",
+    "tfqmrgpux_bsrsv_setShardHints", "tfqmrgpux_bsrsv_getMatrixPartInfo", "tfqmrgpux_bsrsv_setMatrixPart", "tfqmrgpux_bsrsv_getTileBlocks", "tfqmrgpux_tileBlocksFor", "tfqmrgpux_bsrsv_setRhsTrivial", "tfqmrgpux_bsrsv_setEarlyFreeze", "tfqmrgpux_bsrsv_setInitialGuess", "tfqmrgpux_bsrsv_setPreconditioner", "tfqmrgpux_bsrsv_getMixedInfo",
 ]
 FORTRAN_SYMBOLS = [
     "tfqmrgpuprinterror_", "tfqmrgpucreatehandle_", "tfqmrgpudestroyhandle_", "tfqmrgpusetstream_",
@@ -120,6 +120,7 @@ def load():
     lib.tfqmrgpux_bsrsv_setProfiling.restype = st; lib.tfqmrgpux_bsrsv_setProfiling.argtypes = [vp, C.c_int]
     lib.tfqmrgpux_bsrsv_getSolveProfile.restype = st; lib.tfqmrgpux_bsrsv_getSolveProfile.argtypes = [vp, C.POINTER(C.c_double)]
     lib.tfqmrgpux_bsrsv_setOperator.restype = st; lib.tfqmrgpux_bsrsv_setOperator.argtypes = [vp, vp, vp]
+    lib.tfqmrgpux_bsrsv_setPreconditioner.restype = st; lib.tfqmrgpux_bsrsv_setPreconditioner.argtypes = [vp, vp, vp]
     lib.tfqmrgpux_bsrsv_setDevices.restype = st; lib.tfqmrgpux_bsrsv_setDevices.argtypes = [vp, vp, C.c_int, i32p]
     lib.tfqmrgpux_bsrsv_getDevices.restype = st; lib.tfqmrgpux_bsrsv_getDevices.argtypes = [vp, C.POINTER(C.c_int), i32p, C.c_int]
     lib.tfqmrgpux_bsrsv_setShardExchange.restype = st

@@ -181,6 +181,26 @@ class BsrsvPlan:
         self._op_keepalive = cb
         _check(self.lib.tfqmrgpux_bsrsv_setOperator(self.plan, C.cast(cb, C.c_void_p), None), "setOperator")
 
+    def set_preconditioner(self, fn):
+        """Right preconditioner (tfqmrgpux_bsrsv_setPreconditioner): ``fn(z_ptr, x_ptr, state_ptr, expect, stream) -> int`` computes
+        z = P*x on X-shaped device vectors in storage order, like the callback of set_operator; ``None`` removes it."""
+        proto = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p)
+        if fn is None:
+            self._pc_keepalive = None
+            _check(self.lib.tfqmrgpux_bsrsv_setPreconditioner(self.plan, None, None), "setPreconditioner")
+            return
+
+        def trampoline(_ctx, z, x, state, expect, stream):
+            try:
+                return int(fn(int(z or 0), int(x or 0), int(state or 0), int(expect), int(stream or 0)) or 0)
+            except Exception:          # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return L.UNDOCUMENTED_ERROR
+        cb = proto(trampoline)
+        self._pc_keepalive = cb
+        _check(self.lib.tfqmrgpux_bsrsv_setPreconditioner(self.plan, C.cast(cb, C.c_void_p), None), "setPreconditioner")
+
     def plan_info(self) -> dict:
         info = (C.c_int64*16)()
         _check(self.lib.tfqmrgpux_bsrsv_getPlanInfo(self.plan, info), "getPlanInfo")

@@ -576,6 +576,15 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_setOperator(tfqmrgpuBsrsvPlan_t plan, tfqmrgpux
     return TFQMRGPU_STATUS_SUCCESS;
 }
 
+tfqmrgpuStatus_t tfqmrgpux_bsrsv_setPreconditioner(tfqmrgpuBsrsvPlan_t plan, tfqmrgpuxOperator_t op, void *ctx) {
+    if (nullptr == plan) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    Plan &p = *P(plan);
+    if (op && (p.multi || p.mixed)) return TFQ_ERR(TFQMRGPU_NO_IMPLEMENTATION);
+    p.precond = op; p.precond_ctx = op ? ctx : nullptr;
+    plan_drop_graph(p);          // a captured iteration body multiplies v6 itself
+    return TFQMRGPU_STATUS_SUCCESS;
+}
+
 tfqmrgpuStatus_t tfqmrgpux_bsrsv_multiply(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan_t plan, int nrep) {
     if (nullptr == plan || nullptr == handle) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     Plan &p = *P(plan);

@@ -252,7 +252,7 @@ tfqmrgpuStatus_t mixed_solve(Plan &p, cudaStream_t stream, double tolerance, int
     Plan &q = *m.inner;
     if (nullptr == q.pBuffer || !q.configured) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     if (!m.a_ready && p.nnzbA > 0) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);     // setMatrix('A') has not been called
-    if (p.user_op || p.exch.slots) return TFQ_ERR(TFQMRGPU_NO_IMPLEMENTATION);
+    if (p.user_op || p.precond || p.exch.slots) return TFQ_ERR(TFQMRGPU_NO_IMPLEMENTATION);
 
     double *const X = ws<double>(p, p.off_v[1]), *const Y = ws<double>(p, p.off_v[9]);
     int const blockElems = 2*p.LM*p.LN;

@@ -360,6 +360,7 @@ void plan_drop_graph(Plan &p) {
 static void free_configured(Plan &p) {
     plan_drop_graph(p);
     cudaFree(p.d_guess_scratch); p.d_guess_scratch = nullptr;
+    cudaFree(p.d_precond_tmp); p.d_precond_tmp = nullptr;
     cudaFree(p.d_tiles); p.d_tiles = nullptr;
     cudaFree(p.d_coltile); p.d_coltile = nullptr;
     cudaFree(p.d_unit_e0); p.d_unit_e0 = nullptr;

@@ -65,6 +65,15 @@ namespace {
 constexpr int kBodyKernels = 11;
 }
 
+// Right preconditioner (the slot the reference left commented out: core.hxx:37,57 `has_preconditioner`, `vP`): the solver iterates on
+// A*P, every product becomes y = A*(P*x) through the plan's extra vector, and X = P*v1 once the iterations have ended.
+static tfqmrgpuStatus_t apply_precond(Plan &p, void const *x, int expect, cudaStream_t stream)
+{
+    if (nullptr == p.d_precond_tmp) TFQ_CUDA(cudaMalloc((void**)&p.d_precond_tmp, p.vecBytes));
+    int32_t const st = p.precond(p.precond_ctx, p.d_precond_tmp, x, reinterpret_cast<int32_t const*>(&ws<Control const>(p, p.off_ctl)->state), expect, stream);
+    return st ? tfqmrgpuStatus_t(st) : TFQMRGPU_STATUS_SUCCESS;
+}
+
 // one tfQMR iteration (core.hxx:189-233); every kernel checks the device-resident state first and runs only in state RUN
 // (events: nullptr, or four events recorded around the two A*v6 products when profiling)
 tfqmrgpuStatus_t enqueue_iteration(Plan &p, cudaStream_t stream, cudaEvent_t const *events)
@@ -75,18 +84,21 @@ tfqmrgpuStatus_t enqueue_iteration(Plan &p, cudaStream_t stream, cudaEvent_t con
 #define TFQ_DO(call) do { st = (call); if (TFQMRGPU_STATUS_SUCCESS != st) return st; } while (0)
     // plans on the fp16-pair tensor-core product: K1 and K3 write v6 AND its tensor-core operand (TFQMRGPU_XOP_FUSED=0: separate pass)
     static bool const fuse_env = [] { char const *e = std::getenv("TFQMRGPU_XOP_FUSED"); return !(e && '0' == e[0]); }();
-    bool const fused = p.use_tc16 && fuse_env && nullptr == p.user_op;
+    bool const fused = p.use_tc16 && fuse_env && nullptr == p.user_op && nullptr == p.precond;
+    void const *xin = v6;                                              // what the products multiply: v6, or P*v6
     TFQ_DO(fused ? launch_vecop_xop(p, OP_K1, stream) : launch_vecop(p, OP_K1, stream));
+    if (p.precond) { TFQ_DO(apply_precond(p, v6, STATE_RUN, stream)); xin = p.d_precond_tmp; }
     if (events) TFQ_CUDA(cudaEventRecord(events[0], stream));
     TFQ_DO(fused ? launch_spmm_operand_ready(p, v9, v6, STATE_RUN, stream)
-                 : launch_spmm(p, v9, v6, STATE_RUN, stream));         // v9 := A*v6     (core.hxx:198)
+                 : launch_spmm(p, v9, xin, STATE_RUN, stream));        // v9 := A*v6     (core.hxx:198)
     if (events) TFQ_CUDA(cudaEventRecord(events[1], stream));
     TFQ_DO(launch_vecop(p, OP_E1, stream));
     TFQ_DO(launch_vecop(p, OP_K2, stream));
     TFQ_DO(fused ? launch_vecop_xop(p, OP_K3, stream) : launch_vecop(p, OP_K3, stream));
+    if (p.precond) TFQ_DO(apply_precond(p, v6, STATE_RUN, stream));
     if (events) TFQ_CUDA(cudaEventRecord(events[2], stream));
     TFQ_DO(fused ? launch_spmm_operand_ready(p, v8, v6, STATE_RUN, stream)
-                 : launch_spmm(p, v8, v6, STATE_RUN, stream));         // v8 := A*v6     (core.hxx:224)
+                 : launch_spmm(p, v8, xin, STATE_RUN, stream));        // v8 := A*v6     (core.hxx:224)
     if (events) TFQ_CUDA(cudaEventRecord(events[3], stream));
     TFQ_DO(launch_vecop(p, OP_E2, stream));
     TFQ_DO(launch_vecop(p, OP_K4, stream));
@@ -100,7 +112,9 @@ tfqmrgpuStatus_t enqueue_probe(Plan &p, cudaStream_t stream)
     void *const v1 = p.pBuffer + p.off_v[1], *const v9 = p.pBuffer + p.off_v[9];
     tfqmrgpuStatus_t st;
 #define TFQ_DO(call) do { st = (call); if (TFQMRGPU_STATUS_SUCCESS != st) return st; } while (0)
-    TFQ_DO(launch_spmm(p, v9, v1, STATE_PROBE, stream));               // v9 := A*v1     (core.hxx:265)
+    void const *xin = v1;
+    if (p.precond) { TFQ_DO(apply_precond(p, v1, STATE_PROBE, stream)); xin = p.d_precond_tmp; }      // the true residual is A*(P*v1) - b
+    TFQ_DO(launch_spmm(p, v9, xin, STATE_PROBE, stream));              // v9 := A*v1     (core.hxx:265)
     TFQ_DO(launch_add_rhs(p, v9, -1.0, STATE_PROBE, stream));          // v9 -= b        (core.hxx:267)
     TFQ_DO(launch_vecop(p, OP_N3, stream));
 #undef TFQ_DO
@@ -165,6 +179,7 @@ tfqmrgpuStatus_t solve_begin(Plan &p, cudaStream_t stream, double tolerance, int
         return TFQMRGPU_BLOCKSIZE_MISSING + TFQMRGPU_CODE_CHAR*p.LM + TFQMRGPU_CODE_LINE*p.LN;
     if ('z' != p.precision && 'c' != p.precision) return TFQ_ERRC(TFQMRGPU_PRECISION_MISSMATCH, p.precision);
     if (nullptr == p.pBuffer || !p.configured) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+    if (p.precond && p.initial_guess) return TFQ_ERR(TFQMRGPU_NO_IMPLEMENTATION);   // (v1 would mix x0 with the unpreconditioned iterate)
 
     // lazily created host-side resources; every step is retried by the next solve if it fails here
     for (auto &e : p.ev) if (nullptr == e) TFQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -257,7 +272,7 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
     auto mark = [&](int which) { return p.profile ? cudaEventRecord(p.prof_ev[which], stream) : cudaSuccess; };
     TFQ_CUDA(mark(0));
     // (a callback cannot be captured blindly; the exchange hook of a sharded run is a host call per iteration)
-    bool const use_graph = graphs_enabled() && !p.profile && maxIterations > 0 && nullptr == p.user_op && nullptr == p.exch.slots
+    bool const use_graph = graphs_enabled() && !p.profile && maxIterations > 0 && nullptr == p.user_op && nullptr == p.precond && nullptr == p.exch.slots
                            && !(resident_supported(p) && !p.initial_guess);
     if (use_graph && nullptr == p.body_exec) {
         tfqmrgpuStatus_t const gst = build_body_graph(p);
@@ -277,7 +292,7 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
 
     int bodies = 0;
     // small systems: the whole solve in one cooperative launch (resident.cu); the loop below is skipped
-    bool const resident = maxIterations > 0 && !p.initial_guess && resident_supported(p);   // (the resident solver starts from X = 0)
+    bool const resident = maxIterations > 0 && !p.initial_guess && nullptr == p.precond && resident_supported(p);   // (the resident solver starts from X = 0)
     if (resident) {
         st = launch_resident_solve(p, stream, maxIterations);
         if (TFQMRGPU_STATUS_SUCCESS != st) return st;
@@ -303,6 +318,12 @@ tfqmrgpuStatus_t solve(Plan &p, cudaStream_t stream, double tolerance, int maxIt
         TFQ_CUDA(cudaMemcpyAsync(&p.h_ctl[slot], d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, stream));
         TFQ_CUDA(cudaEventRecord(p.ev[slot], stream));
         ++bodies;
+    }
+    if (p.precond && maxIterations > 0) {      // X = P*v1 (the speculative bodies behind DONE did not touch v1)
+        st = apply_precond(p, p.pBuffer + p.off_v[1], -1, stream);
+        if (TFQMRGPU_STATUS_SUCCESS != st) return st;
+        TFQ_CUDA(cudaMemcpyAsync(p.pBuffer + p.off_v[1], p.d_precond_tmp, p.vecBytes, cudaMemcpyDeviceToDevice, stream));
+        launches += 1;
     }
     Control &fin = p.h_ctl[6];
     TFQ_CUDA(cudaMemcpyAsync(&fin, d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, stream));

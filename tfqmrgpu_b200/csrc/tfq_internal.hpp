@@ -109,6 +109,9 @@ struct Plan {
     size_t tile_blocks_hint = 0;             // > 0: forced tile size (dev / experiments); the default rule is per block column
     tfqmrgpuxOperator_t user_op = nullptr;   // user-defined operator instead of the block-sparse product (ext header)
     void *user_ctx = nullptr;
+    tfqmrgpuxOperator_t precond = nullptr;   // right preconditioner z = P*x as a C callback (tfqmrgpux_bsrsv_setPreconditioner): the solver iterates on A*P
+    void *precond_ctx = nullptr;
+    char *d_precond_tmp = nullptr;           // one X-shaped vector owned by the plan: P*v6 / P*v1 (the reference's vP, core.hxx:57)
     bool use_small = false;           // LM <= 8: register-staged batches of entries instead of the bulk-copy ring (spmm.cu)
     uint32_t *d_unit_e0 = nullptr;    // [nUnits+1] first entry of every unit
     uint32_t *d_unit_y = nullptr;     // [nUnits*gmax] storage index of the unit's Y blocks (kNoBlock = none)
