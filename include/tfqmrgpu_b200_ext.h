@@ -123,7 +123,7 @@ tfqmrgpuStatus_t tfqmrgpux_bsrsv_setEarlyFreeze(tfqmrgpuBsrsvPlan_t plan, int on
  * setDevices, setOperator or setMatrixPart.  TFQMRGPU_MIXED=0 restores the reference's refusal; TFQMRGPU_MIXED_INNER_TOL (default
  * 1e-3), TFQMRGPU_MIXED_INNER_ITER (default max(40, maxIterations/4)) and TFQMRGPU_MIXED_FREEZE (default 1: the fp32 passes use the
  * per-right-hand-side freeze of setEarlyFreeze) tune the passes.  Measured on one GPU's share of BASELINE config 4 (32^3 block rows,
- * 32x32 blocks, 128 right-hand sides, sigma 1, tol 1e-9): 'z' 2125 ms (29 iterations), 'm' 736 ms (3 passes, 42 fp32 iterations),
+ * 32x32 blocks, 128 right-hand sides, sigma 1, tol 1e-9): 'z' 2125 ms (29 iterations), 'm' 759 ms (3 passes, 42 fp32 iterations),
  * solutions equal to 2e-12 (tests/tools/bench_mixed.py, profiles/r02_bench_mixed.json).
  *
  * setInitialGuess (every single-device plan): with on != 0 solve starts from the X uploaded with setMatrix('X') - or, on a second

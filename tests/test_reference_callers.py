@@ -197,3 +197,19 @@ def test_config3_full_size_vs_reference_cuda_build():
     assert np.abs(X - r["X"]).max() <= 50*tol*np.abs(r["X"]).max()
     torch.cuda.empty_cache()
 
+
+
+def test_c_example_mixed_precision_one_character_change():
+    """examples/mixed_precision.c: a plain C caller (tfqmrgpu.h only) solves the same system with precision 'z' and with 'm' - the
+    precision the reference documents (tfqmrgpu.h:72) and refuses (tfqmrgpu.cu:42-44) - and compares the solutions."""
+    exe = os.path.join(ROOT, "examples", "_build", "mixed_precision")
+    if not os.path.exists(exe):
+        pytest.skip("examples/_build/mixed_precision not built (make -C examples)")
+    for args in (["64", "16", "2", "1e-10"], ["40", "32", "3", "1e-9"], ["30", "8", "1", "1e-10"]):
+        out = subprocess.run([exe, *args], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and "mixed_precision: OK" in out.stdout, out.stdout + out.stderr
+        m = re.search(r"precision m: status 0, (\d+) iterations, residual ([0-9.e+-]+)", out.stdout)
+        assert m and int(m.group(1)) > 0 and float(m.group(2)) <= float(args[3]), out.stdout
+    env = dict(os.environ, TFQMRGPU_MIXED="0")           # the reference's behaviour: 'm' is refused with PRECISION_MISSMATCH (16)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode != 0 and "status 1090" in out.stdout.replace(",", ""), out.stdout + out.stderr

@@ -132,6 +132,7 @@ void mixed_destroy(Plan &p)
     if (m->d_colstart) cudaFree(m->d_colstart);
     delete m;
     p.mixed = nullptr;
+    p.lean_vectors = false;
 }
 
 Plan* mixed_inner(Plan const &p) { return p.mixed ? p.mixed->inner : nullptr; }
@@ -140,11 +141,12 @@ int   mixed_passes(Plan const &p) { return p.mixed ? p.mixed->passes : 0; }
 // bufferSize(..., 'm'): the fp64 plan, the fp32 plan and the scratch of the refinement in ONE caller-owned workspace
 tfqmrgpuStatus_t mixed_buffer_size(Plan &p, cudaStream_t stream, int LM, int LN, size_t *bytes)
 {
+    p.lean_vectors = true;                 // X, Y and a scratch vector: the iteration's v4..v7 live in the fp32 plan only
     tfqmrgpuStatus_t st = plan_configure(p, stream, LM, LN, 'z');
-    if (TFQMRGPU_STATUS_SUCCESS != st) return st;
+    if (TFQMRGPU_STATUS_SUCCESS != st) { p.lean_vectors = (nullptr != p.mixed); return st; }
     if (nullptr == p.mixed) {
         p.mixed = new (std::nothrow) MixedPlan();
-        if (nullptr == p.mixed) return TFQ_ERR(TFQMRGPU_STATUS_ALLOCATION_FAILED);
+        if (nullptr == p.mixed) { p.lean_vectors = false; return TFQ_ERR(TFQMRGPU_STATUS_ALLOCATION_FAILED); }
     }
     MixedPlan &m = *p.mixed;
     m.a_ready = false;

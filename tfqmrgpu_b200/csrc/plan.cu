@@ -590,7 +590,12 @@ tfqmrgpuStatus_t plan_configure(Plan &p, cudaStream_t stream, int LM, int LN, ch
         p.vecBytes = size_t(p.nnzbX)*blockBytes;
         // v1 (X) first, then v4..v9 contiguous so that one memset clears them (core.hxx:114-125)
         p.off_v[1] = take(p.vecBytes);
-        for (int v = 4; v <= 9; ++v) p.off_v[v] = take(p.vecBytes);
+        if (p.lean_vectors) {      // the fp64 side of a mixed-precision plan (mixed.cu) never iterates: X, the product and one scratch vector
+            p.off_v[8] = take(p.vecBytes); p.off_v[9] = take(p.vecBytes);
+            for (int v = 4; v <= 7; ++v) p.off_v[v] = p.off_v[9];
+        } else {
+            for (int v = 4; v <= 9; ++v) p.off_v[v] = take(p.vecBytes);
+        }
         if (p.use_tc16) p.off_xop = take(p.vecBytes);                // fp16 pairs: the same 4 bytes per element
         p.off_v[3]  = take(size_t(p.nnzbX)*2*LM*LN*sizeof(float));   // v3 is always float (core.hxx:60)
         p.off_B     = take(size_t(p.nnzbB)*blockBytes);

@@ -95,6 +95,7 @@ struct Plan {
     bool use_dmma = false;            // complex fp64 product on the FP64 tensor pipe (spmm_dmma.cu)
     Exchange exch;
     struct MultiPlan *multi = nullptr;       // in-process multi-GPU plan (multi.cu): this Plan is then only the global analysis
+    bool lean_vectors = false;               // workspace layout without v4..v7 (the fp64 side of a mixed plan)
     struct MixedPlan *mixed = nullptr;       // precision 'm' (mixed.cu): this Plan is the fp64 side (precision == 'z') of a refinement around an fp32 plan
     int initial_guess = 0;                  // opt-in: solve starts from v1 instead of zero (tfqmrgpux_bsrsv_setInitialGuess)
     double *d_guess_scratch = nullptr; double guess_flops = 0;
