@@ -69,7 +69,9 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_destroyPlan(tfqmrgpuHandle_t handle, tfqmrgpuBsr
 
 /* ---- workspace size (ref tfqmrgpu.h:66-73, tfqmrgpu.cu:364-412) ---------------------------------
  * Requires ldA == blockDim, ldA <= ldB == RhsBlockDim.  precision 'c'/'f' -> complex<float>,
- * 'z'/'d' -> complex<double>, 'm' is accepted here and rejected at solve like the reference. */
+ * 'z'/'d' -> complex<double>.  'm' ("start with float and converge double", ref tfqmrgpu.h:72): the reference accepts it here and
+ * rejects it at solve (tfqmrgpu.cu:42-44); this library implements it - double data in and out, complex<float> iterations inside an
+ * fp64 refinement loop, see tfqmrgpu_b200_ext.h - unless TFQMRGPU_MIXED=0 asks for the reference's PRECISION_MISSMATCH. */
 tfqmrgpuStatus_t tfqmrgpu_bsrsv_bufferSize(tfqmrgpuHandle_t handle,
     tfqmrgpuBsrsvPlan_t plan,
     int const ldA, int const blockDim, int const ldB, int const RhsBlockDim,
