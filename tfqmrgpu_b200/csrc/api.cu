@@ -384,6 +384,7 @@ tfqmrgpuStatus_t tfqmrgpu_bsrsv_solve(tfqmrgpuHandle_t handle, tfqmrgpuBsrsvPlan
     if (nullptr == plan || nullptr == handle) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
     if (P(plan)->multi) {
         if (nullptr == P(plan)->pBuffer || !P(plan)->configured) return TFQ_ERR(TFQMRGPU_POINTER_INVALID);
+        if (P(plan)->initial_guess || P(plan)->precond) return TFQ_ERR(TFQMRGPU_NO_IMPLEMENTATION);   // single-device plans only
         return multi_solve(*P(plan), threshold, maxIterations);
     }
     if (P(plan)->mixed) return mixed_solve(*P(plan), static_cast<Handle*>(handle)->stream, threshold, maxIterations);
